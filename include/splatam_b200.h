@@ -1,0 +1,151 @@
+/*
+ * splatam_b200.h -- C-ABI of the B200-native differentiable 3D-Gaussian rasterizer.
+ *
+ * This is the drop-in boundary for the ONE hot path SplaTAM has: the
+ * `diff_gaussian_rasterization._C` extension.  Each entry point below names the
+ * reference interface it replaces (paths relative to
+ * /root/reference/diff-gaussian-rasterization-w-depth.git/, "X/").
+ *
+ *   reference                                                     this header
+ *   ------------------------------------------------------------  -------------------------
+ *   rasterize_gaussians          X/rasterize_points.h:18-37       sb_forward_geometry + sb_forward_render
+ *     -> Rasterizer::forward     X/cuda_rasterizer/rasterizer.h:35-59
+ *   rasterize_gaussians_backward X/rasterize_points.h:39-60       sb_backward
+ *     -> Rasterizer::backward    X/cuda_rasterizer/rasterizer.h:61-89
+ *   mark_visible                 X/rasterize_points.h:62-65       sb_mark_visible
+ *     -> Rasterizer::markVisible X/cuda_rasterizer/rasterizer.h:27-33
+ *   resize callbacks std::function<char*(size_t)>                 sb_*_workspace_bytes + caller-owned
+ *                                X/rasterize_points.cu:27-33      device workspaces
+ *   GaussianRasterizationSettings X/diff_gaussian_rasterization/__init__.py:134-145   sb_settings
+ *
+ * Conventions
+ *   - plain C types only; every pointer marked "dev" is a DEVICE pointer owned by the caller.
+ *   - NULL means "not provided" (the reference passes empty tensors whose data_ptr() is null,
+ *     X/diff_gaussian_rasterization/__init__.py:173-183).
+ *   - every call enqueues work on `stream` (a cudaStream_t passed as void*); only
+ *     sb_forward_geometry synchronises that stream (it returns num_rendered to the host, like
+ *     X/cuda_rasterizer/rasterizer_impl.cu:282).
+ *   - return value: 0 = SB_OK, otherwise an sb_status code; sb_status_string() names it.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry returns SB_ERR_CUDA.
+ */
+#ifndef SPLATAM_B200_H_INCLUDED
+#define SPLATAM_B200_H_INCLUDED
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SB_ABI_VERSION 1
+#define SB_TILE 16 /* BLOCK_X == BLOCK_Y == 16, X/cuda_rasterizer/config.h:16-17 (part of the key contract) */
+#define SB_CHANNELS 3 /* NUM_CHANNELS, X/cuda_rasterizer/config.h:15 */
+
+typedef enum sb_status {
+    SB_OK = 0,
+    SB_ERR_BAD_ARG = 1,      /* null/negative/inconsistent argument                     */
+    SB_ERR_WORKSPACE = 2,    /* a caller-provided workspace is too small                */
+    SB_ERR_CUDA = 3,         /* a CUDA runtime call or kernel launch failed             */
+    SB_ERR_UNSUPPORTED = 4   /* feature of the reference API not built  */
+} sb_status;
+
+/* Mirror of GaussianRasterizationSettings (X/diff_gaussian_rasterization/__init__.py:134-145).
+ * Matrices are the 16 floats of the reference's [1,4,4] tensors, read exactly as the reference
+ * kernels read them (element k = flat index k; X/cuda_rasterizer/auxiliary.h:58-77). */
+typedef struct sb_settings {
+    int32_t image_height;
+    int32_t image_width;
+    float tanfovx;
+    float tanfovy;
+    const float* bg;          /* dev [3]  */
+    float scale_modifier;
+    const float* viewmatrix;  /* dev [16] */
+    const float* projmatrix;  /* dev [16] */
+    int32_t sh_degree;
+    const float* campos;      /* dev [3]  */
+    int32_t prefiltered;
+} sb_settings;
+
+int sb_abi_version(void);
+const char* sb_status_string(int status);
+/* Text of the last CUDA error seen by this thread's most recent failing call ("" if none). */
+const char* sb_last_cuda_error(void);
+
+/* ---- workspace sizing (replaces required<GeometryState/ImageState/BinningState>,
+ *      X/cuda_rasterizer/rasterizer_impl.h:63-72) -------------------------------------- */
+int sb_geometry_workspace_bytes(int P, size_t* bytes);
+int sb_image_workspace_bytes(int width, int height, size_t* bytes);
+int sb_binning_workspace_bytes(int num_rendered, int width, int height, size_t* bytes);
+int sb_backward_workspace_bytes(int P, size_t* bytes);
+
+/* ---- forward, stage 1: per-Gaussian projection + depth ordering -----------------------
+ * FORWARD::preprocess + InclusiveSum + num_rendered readback
+ * (X/cuda_rasterizer/forward.cu:155-256, rasterizer_impl.cu:248-282).
+ * means3D [P,3], opacities [P], scales [P,3], rotations [P,4] (or cov3D_precomp [P,6]).
+ * Writes radii [P] (int32) and *num_rendered (host).  Synchronises `stream`. */
+int sb_forward_geometry(const sb_settings* s, int P,
+                        const float* means3D, const float* opacities,
+                        const float* scales, const float* rotations,
+                        const float* cov3D_precomp,
+                        int32_t* radii,
+                        void* geom_ws, size_t geom_ws_bytes,
+                        int* num_rendered,
+                        void* stream);
+
+/* ---- forward, stage 2: tile duplication + sort + alpha-composite ------------------------
+ * duplicateWithKeys + SortPairs + identifyTileRanges + FORWARD::render
+ * (X/cuda_rasterizer/rasterizer_impl.cu:284-337, forward.cu:261-393).
+ * colors [P,3] (colors_precomp).  out_color [3,H,W], out_depth [1,H,W]. */
+int sb_forward_render(const sb_settings* s, int P, int num_rendered,
+                      const float* colors,
+                      const void* geom_ws, size_t geom_ws_bytes,
+                      void* binning_ws, size_t binning_ws_bytes,
+                      void* image_ws, size_t image_ws_bytes,
+                      float* out_color, float* out_depth,
+                      void* stream);
+
+/* ---- backward ---------------------------------------------------------------------------
+ * BACKWARD::render + BACKWARD::preprocess (X/cuda_rasterizer/backward.cu:399-657).
+ * dL_dout_color [3,H,W].  Outputs are fully overwritten (no pre-zeroing needed):
+ * dL_dmeans3D [P,3], dL_dmeans2D [P,3], dL_dcolors [P,3], dL_dopacity [P],
+ * dL_dscales [P,3], dL_drotations [P,4]; dL_dcov3D [P,6] may be NULL. */
+int sb_backward(const sb_settings* s, int P, int num_rendered,
+                const float* means3D, const float* colors,
+                const float* scales, const float* rotations,
+                const float* cov3D_precomp,
+                const int32_t* radii,
+                const void* geom_ws, size_t geom_ws_bytes,
+                const void* binning_ws, size_t binning_ws_bytes,
+                const void* image_ws, size_t image_ws_bytes,
+                void* bwd_ws, size_t bwd_ws_bytes,
+                const float* dL_dout_color,
+                float* dL_dmeans3D, float* dL_dmeans2D, float* dL_dcolors,
+                float* dL_dopacity, float* dL_dscales, float* dL_drotations,
+                float* dL_dcov3D,
+                void* stream);
+
+/* ---- markVisible (X/cuda_rasterizer/rasterizer_impl.cu:54-66,141-153) ------------------- */
+int sb_mark_visible(int P, const float* means3D, const float* viewmatrix,
+                    const float* projmatrix, uint8_t* present, void* stream);
+
+/* ---- inspection (parity tests only): the intermediates the reference keeps in its
+ *      geometry/binning/image byte buffers (X/cuda_rasterizer/rasterizer_impl.cu:155-194). ---
+ * Any output pointer may be NULL.  All outputs are device pointers.
+ *   depths [P] f32, means2D [P,2] f32, conic_opacity [P,4] f32, tiles_touched [P] u32 */
+int sb_export_geometry(int P, const void* geom_ws, size_t geom_ws_bytes,
+                       float* depths, float* means2D, float* conic_opacity,
+                       uint32_t* tiles_touched, void* stream);
+/*   keys [R] u64 = (tile<<32)|depth_bits, point_list [R] u32, both in sorted order;
+ *   ranges [tiles,2] u32, final_T [H*W] f32, n_contrib [H*W] u32 */
+int sb_export_binning(const sb_settings* s, int P, int num_rendered,
+                      const void* geom_ws, size_t geom_ws_bytes,
+                      const void* binning_ws, size_t binning_ws_bytes,
+                      const void* image_ws, size_t image_ws_bytes,
+                      uint64_t* keys, uint32_t* point_list, uint32_t* ranges,
+                      float* final_T, uint32_t* n_contrib, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPLATAM_B200_H_INCLUDED */

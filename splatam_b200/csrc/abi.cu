@@ -1,0 +1,264 @@
+// abi.cu -- the extern "C" boundary declared in include/splatam_b200.h: argument checks, workspace
+// carving, stage sequencing.  No torch, no STL types in any signature.
+#include "common.cuh"
+#include <string.h>
+#include <stdio.h>
+
+namespace sb {
+
+static thread_local char g_cuda_error[512] = "";
+
+void set_cuda_error(cudaError_t e, const char* where) {
+    snprintf(g_cuda_error, sizeof(g_cuda_error), "%s: %s (%s)", where, cudaGetErrorName(e), cudaGetErrorString(e));
+}
+
+GeometryWs carve_geometry(void* ws, int P, size_t* total) {
+    Carver c(ws);
+    GeometryWs g;
+    const size_t n = (size_t)(P > 0 ? P : 1);
+    g.header = c.take<int32_t>(64);
+    g.depth_key = c.take<uint32_t>(n);
+    g.tiles_touched = c.take<uint32_t>(n);
+    g.geomA = c.take<float4>(n);
+    g.geomB = c.take<float4>(n);
+    g.rect = c.take<uint2>(n);
+    g.iota = c.take<uint32_t>(n);
+    g.sorted_key = c.take<uint32_t>(n);
+    g.sorted_idx = c.take<uint32_t>(n);
+    g.offsets = c.take<uint32_t>(n);
+    g.cub_temp_bytes = geometry_cub_temp_bytes((int)n);
+    g.cub_temp = c.take<char>(g.cub_temp_bytes);
+    if (total) *total = c.used();
+    return g;
+}
+
+BinningWs carve_binning(void* ws, int R, int tiles, size_t* total) {
+    Carver c(ws);
+    BinningWs b;
+    const size_t n = (size_t)(R > 0 ? R : 1);
+    const bool keys16 = higher_msb((uint32_t)tiles) <= 16;
+    b.tile_unsorted = c.take<uint32_t>(keys16 ? (n + 1) / 2 : n);
+    b.val_unsorted = c.take<uint32_t>(n);
+    b.tile_sorted = c.take<uint32_t>(keys16 ? (n + 1) / 2 : n);
+    b.point_list = c.take<uint32_t>(n);
+    b.recA = c.take<float4>(n);
+    b.recB = c.take<float4>(n);
+    b.recC = c.take<float4>(n);
+    b.cub_temp_bytes = binning_cub_temp_bytes((int)n, keys16);
+    b.cub_temp = c.take<char>(b.cub_temp_bytes);
+    if (total) *total = c.used();
+    return b;
+}
+
+ImageWs carve_image(void* ws, int W, int H, size_t* total) {
+    Carver c(ws);
+    ImageWs img;
+    const size_t tiles = (size_t)((W + kTile - 1) / kTile) * ((H + kTile - 1) / kTile);
+    img.ranges = c.take<uint2>(tiles);
+    img.final_T = c.take<float>((size_t)W * H);
+    img.n_contrib = c.take<uint32_t>((size_t)W * H);
+    if (total) *total = c.used();
+    return img;
+}
+
+static bool settings_ok(const sb_settings* s) {
+    return s && s->image_width > 0 && s->image_height > 0 && s->bg && s->viewmatrix && s->projmatrix &&
+           (s->image_width + kTile - 1) / kTile <= 65535 && (s->image_height + kTile - 1) / kTile <= 65535;
+}
+static int tiles_of(const sb_settings* s) {
+    return ((s->image_width + kTile - 1) / kTile) * ((s->image_height + kTile - 1) / kTile);
+}
+
+// Small helper kernels for the inspection entry points.
+__global__ void export_geometry_kernel(int P, const uint32_t* depth_key, const float4* geomA, const float4* geomB,
+                                       const uint32_t* tiles_touched, float* depths, float* means2D,
+                                       float* conic_opacity, uint32_t* tt) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    const bool vis = tiles_touched[i] != 0u;
+    if (depths) depths[i] = vis ? __uint_as_float(depth_key[i]) : 0.f;
+    if (means2D) { means2D[2 * i] = vis ? geomA[i].x : 0.f; means2D[2 * i + 1] = vis ? geomA[i].y : 0.f; }
+    if (conic_opacity) reinterpret_cast<float4*>(conic_opacity)[i] = geomB[i];
+    if (tt) tt[i] = tiles_touched[i];
+}
+template <typename KeyT>
+__global__ void export_keys_kernel(int R, const KeyT* tile_sorted, const uint32_t* point_list,
+                                   const uint32_t* depth_key, uint64_t* keys, uint32_t* list) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= R) return;
+    const uint32_t g = point_list[i];
+    if (keys) keys[i] = ((uint64_t)tile_sorted[i] << 32) | (uint64_t)depth_key[g];
+    if (list) list[i] = g;
+}
+
+}  // namespace sb
+
+using namespace sb;
+
+extern "C" {
+
+int sb_abi_version(void) { return SB_ABI_VERSION; }
+
+const char* sb_status_string(int status) {
+    switch (status) {
+        case SB_OK: return "SB_OK";
+        case SB_ERR_BAD_ARG: return "SB_ERR_BAD_ARG";
+        case SB_ERR_WORKSPACE: return "SB_ERR_WORKSPACE";
+        case SB_ERR_CUDA: return "SB_ERR_CUDA";
+        case SB_ERR_UNSUPPORTED: return "SB_ERR_UNSUPPORTED";
+        default: return "SB_ERR_UNKNOWN";
+    }
+}
+
+const char* sb_last_cuda_error(void) { return g_cuda_error; }
+
+int sb_geometry_workspace_bytes(int P, size_t* bytes) {
+    if (P < 0 || !bytes) return SB_ERR_BAD_ARG;
+    carve_geometry(nullptr, P, bytes);
+    return SB_OK;
+}
+int sb_image_workspace_bytes(int width, int height, size_t* bytes) {
+    if (width <= 0 || height <= 0 || !bytes) return SB_ERR_BAD_ARG;
+    carve_image(nullptr, width, height, bytes);
+    return SB_OK;
+}
+int sb_binning_workspace_bytes(int num_rendered, int width, int height, size_t* bytes) {
+    if (num_rendered < 0 || width <= 0 || height <= 0 || !bytes) return SB_ERR_BAD_ARG;
+    const int tiles = ((width + kTile - 1) / kTile) * ((height + kTile - 1) / kTile);
+    carve_binning(nullptr, num_rendered, tiles, bytes);
+    return SB_OK;
+}
+int sb_backward_workspace_bytes(int P, size_t* bytes) {
+    if (P < 0 || !bytes) return SB_ERR_BAD_ARG;
+    *bytes = ((size_t)(P > 0 ? P : 1) * kAccumStride * sizeof(float) + kAlign - 1) / kAlign * kAlign;
+    return SB_OK;
+}
+
+int sb_forward_geometry(const sb_settings* s, int P, const float* means3D, const float* opacities,
+                        const float* scales, const float* rotations, const float* cov3D_precomp,
+                        int32_t* radii, void* geom_ws, size_t geom_ws_bytes, int* num_rendered, void* stream) {
+    if (!settings_ok(s) || P < 0 || !num_rendered) return SB_ERR_BAD_ARG;
+    *num_rendered = 0;
+    if (P == 0) return SB_OK;  // rasterize_points.cu:81 -- nothing launched for an empty scene
+    if (!means3D || !opacities || !radii || !geom_ws) return SB_ERR_BAD_ARG;
+    if (!cov3D_precomp && (!scales || !rotations)) return SB_ERR_BAD_ARG;
+    if (s->sh_degree != 0) return SB_ERR_UNSUPPORTED;
+    size_t need = 0;
+    GeometryWs g = carve_geometry(geom_ws, P, &need);
+    if (geom_ws_bytes < need) return SB_ERR_WORKSPACE;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int rc = launch_project(*s, P, means3D, opacities, scales, rotations, cov3D_precomp, radii, g, st);
+    if (rc != SB_OK) return rc;
+    rc = launch_depth_order(P, g, st);
+    if (rc != SB_OK) return rc;
+    uint32_t R = 0;
+    SB_CUDA_CHECK(cudaMemcpyAsync(&R, g.offsets + (P - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    SB_CUDA_CHECK(cudaStreamSynchronize(st));
+    if (R > 0x7fffffffu) return SB_ERR_WORKSPACE;
+    *num_rendered = (int)R;
+    return SB_OK;
+}
+
+int sb_forward_render(const sb_settings* s, int P, int num_rendered, const float* colors,
+                      const void* geom_ws, size_t geom_ws_bytes, void* binning_ws, size_t binning_ws_bytes,
+                      void* image_ws, size_t image_ws_bytes, float* out_color, float* out_depth, void* stream) {
+    if (!settings_ok(s) || P < 0 || num_rendered < 0 || !image_ws || !out_color || !out_depth) return SB_ERR_BAD_ARG;
+    if (P > 0 && (!colors || !geom_ws)) return SB_ERR_BAD_ARG;
+    if (num_rendered > 0 && !binning_ws) return SB_ERR_BAD_ARG;
+    size_t need = 0;
+    GeometryWs g = carve_geometry(const_cast<void*>(geom_ws), P, &need);
+    if (P > 0 && geom_ws_bytes < need) return SB_ERR_WORKSPACE;
+    BinningWs b = carve_binning(binning_ws, num_rendered, tiles_of(s), &need);
+    if (num_rendered > 0 && binning_ws_bytes < need) return SB_ERR_WORKSPACE;
+    ImageWs img = carve_image(image_ws, s->image_width, s->image_height, &need);
+    if (image_ws_bytes < need) return SB_ERR_WORKSPACE;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int rc = launch_binning(*s, P, num_rendered, colors, g, b, img, st);
+    if (rc != SB_OK) return rc;
+    return launch_blend_forward(*s, num_rendered, g, b, img, out_color, out_depth, st);
+}
+
+int sb_backward(const sb_settings* s, int P, int num_rendered, const float* means3D, const float* colors,
+                const float* scales, const float* rotations, const float* cov3D_precomp, const int32_t* radii,
+                const void* geom_ws, size_t geom_ws_bytes, const void* binning_ws, size_t binning_ws_bytes,
+                const void* image_ws, size_t image_ws_bytes, void* bwd_ws, size_t bwd_ws_bytes,
+                const float* dL_dout_color, float* dL_dmeans3D, float* dL_dmeans2D, float* dL_dcolors,
+                float* dL_dopacity, float* dL_dscales, float* dL_drotations, float* dL_dcov3D, void* stream) {
+    (void)geom_ws; (void)geom_ws_bytes;
+    if (!settings_ok(s) || P < 0 || num_rendered < 0) return SB_ERR_BAD_ARG;
+    if (P == 0) return SB_OK;
+    if (!means3D || !colors || !radii || !image_ws || !bwd_ws || !dL_dout_color || !dL_dmeans3D ||
+        !dL_dmeans2D || !dL_dcolors || !dL_dopacity)
+        return SB_ERR_BAD_ARG;
+    if (!cov3D_precomp && (!scales || !rotations || !dL_dscales || !dL_drotations)) return SB_ERR_BAD_ARG;
+    if (num_rendered > 0 && !binning_ws) return SB_ERR_BAD_ARG;
+    size_t need = 0;
+    BinningWs b = carve_binning(const_cast<void*>(binning_ws), num_rendered, tiles_of(s), &need);
+    if (num_rendered > 0 && binning_ws_bytes < need) return SB_ERR_WORKSPACE;
+    ImageWs img = carve_image(const_cast<void*>(image_ws), s->image_width, s->image_height, &need);
+    if (image_ws_bytes < need) return SB_ERR_WORKSPACE;
+    sb_backward_workspace_bytes(P, &need);
+    if (bwd_ws_bytes < need) return SB_ERR_WORKSPACE;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    float* accum = static_cast<float*>(bwd_ws);
+    SB_CUDA_CHECK(cudaMemsetAsync(accum, 0, (size_t)P * kAccumStride * sizeof(float), st));
+    int rc = launch_blend_backward(*s, num_rendered, b, img, dL_dout_color, accum, st);
+    if (rc != SB_OK) return rc;
+    return launch_geometry_backward(*s, P, means3D, colors, scales, rotations, cov3D_precomp, radii, accum,
+                                    dL_dmeans3D, dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dscales,
+                                    dL_drotations, dL_dcov3D, st);
+}
+
+int sb_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,
+                    uint8_t* present, void* stream) {
+    (void)projmatrix;  // the reference's test only uses the view matrix (auxiliary.h:154)
+    if (P < 0) return SB_ERR_BAD_ARG;
+    if (P == 0) return SB_OK;
+    if (!means3D || !viewmatrix || !present) return SB_ERR_BAD_ARG;
+    return launch_mark_visible(P, means3D, viewmatrix, present, static_cast<cudaStream_t>(stream));
+}
+
+int sb_export_geometry(int P, const void* geom_ws, size_t geom_ws_bytes, float* depths, float* means2D,
+                       float* conic_opacity, uint32_t* tiles_touched, void* stream) {
+    if (P <= 0 || !geom_ws) return SB_ERR_BAD_ARG;
+    size_t need = 0;
+    GeometryWs g = carve_geometry(const_cast<void*>(geom_ws), P, &need);
+    if (geom_ws_bytes < need) return SB_ERR_WORKSPACE;
+    export_geometry_kernel<<<(P + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        P, g.depth_key, g.geomA, g.geomB, g.tiles_touched, depths, means2D, conic_opacity, tiles_touched);
+    SB_LAUNCH_CHECK("export_geometry_kernel");
+    return SB_OK;
+}
+
+int sb_export_binning(const sb_settings* s, int P, int num_rendered, const void* geom_ws, size_t geom_ws_bytes,
+                      const void* binning_ws, size_t binning_ws_bytes, const void* image_ws,
+                      size_t image_ws_bytes, uint64_t* keys, uint32_t* point_list, uint32_t* ranges,
+                      float* final_T, uint32_t* n_contrib, void* stream) {
+    if (!settings_ok(s) || P <= 0 || num_rendered < 0 || !geom_ws || !image_ws) return SB_ERR_BAD_ARG;
+    size_t need = 0;
+    GeometryWs g = carve_geometry(const_cast<void*>(geom_ws), P, &need);
+    if (geom_ws_bytes < need) return SB_ERR_WORKSPACE;
+    const int tiles = tiles_of(s);
+    BinningWs b = carve_binning(const_cast<void*>(binning_ws), num_rendered, tiles, &need);
+    if (num_rendered > 0 && (!binning_ws || binning_ws_bytes < need)) return SB_ERR_WORKSPACE;
+    ImageWs img = carve_image(const_cast<void*>(image_ws), s->image_width, s->image_height, &need);
+    if (image_ws_bytes < need) return SB_ERR_WORKSPACE;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (num_rendered > 0 && (keys || point_list)) {
+        const int R = num_rendered;
+        if (higher_msb((uint32_t)tiles) <= 16)
+            export_keys_kernel<uint16_t><<<(R + 255) / 256, 256, 0, st>>>(
+                R, reinterpret_cast<const uint16_t*>(b.tile_sorted), b.point_list, g.depth_key, keys, point_list);
+        else
+            export_keys_kernel<uint32_t><<<(R + 255) / 256, 256, 0, st>>>(R, b.tile_sorted, b.point_list,
+                                                                          g.depth_key, keys, point_list);
+        SB_LAUNCH_CHECK("export_keys_kernel");
+    }
+    const size_t hw = (size_t)s->image_width * s->image_height;
+    if (ranges) SB_CUDA_CHECK(cudaMemcpyAsync(ranges, img.ranges, sizeof(uint2) * (size_t)tiles, cudaMemcpyDeviceToDevice, st));
+    if (final_T) SB_CUDA_CHECK(cudaMemcpyAsync(final_T, img.final_T, sizeof(float) * hw, cudaMemcpyDeviceToDevice, st));
+    if (n_contrib) SB_CUDA_CHECK(cudaMemcpyAsync(n_contrib, img.n_contrib, sizeof(uint32_t) * hw, cudaMemcpyDeviceToDevice, st));
+    return SB_OK;
+}
+
+}  // extern "C"
