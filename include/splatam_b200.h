@@ -38,6 +38,12 @@
 extern "C" {
 #endif
 
+#if defined(__GNUC__)
+#define SB_API __attribute__((visibility("default")))
+#else
+#define SB_API
+#endif
+
 #define SB_ABI_VERSION 1
 #define SB_TILE 16 /* BLOCK_X == BLOCK_Y == 16, X/cuda_rasterizer/config.h:16-17 (part of the key contract) */
 #define SB_CHANNELS 3 /* NUM_CHANNELS, X/cuda_rasterizer/config.h:15 */
@@ -67,24 +73,24 @@ typedef struct sb_settings {
     int32_t prefiltered;
 } sb_settings;
 
-int sb_abi_version(void);
-const char* sb_status_string(int status);
+SB_API int sb_abi_version(void);
+SB_API const char* sb_status_string(int status);
 /* Text of the last CUDA error seen by this thread's most recent failing call ("" if none). */
-const char* sb_last_cuda_error(void);
+SB_API const char* sb_last_cuda_error(void);
 
 /* ---- workspace sizing (replaces required<GeometryState/ImageState/BinningState>,
  *      X/cuda_rasterizer/rasterizer_impl.h:63-72) -------------------------------------- */
-int sb_geometry_workspace_bytes(int P, size_t* bytes);
-int sb_image_workspace_bytes(int width, int height, size_t* bytes);
-int sb_binning_workspace_bytes(int num_rendered, int width, int height, size_t* bytes);
-int sb_backward_workspace_bytes(int P, size_t* bytes);
+SB_API int sb_geometry_workspace_bytes(int P, size_t* bytes);
+SB_API int sb_image_workspace_bytes(int width, int height, size_t* bytes);
+SB_API int sb_binning_workspace_bytes(int num_rendered, int width, int height, size_t* bytes);
+SB_API int sb_backward_workspace_bytes(int P, size_t* bytes);
 
 /* ---- forward, stage 1: per-Gaussian projection + depth ordering -----------------------
  * FORWARD::preprocess + InclusiveSum + num_rendered readback
  * (X/cuda_rasterizer/forward.cu:155-256, rasterizer_impl.cu:248-282).
  * means3D [P,3], opacities [P], scales [P,3], rotations [P,4] (or cov3D_precomp [P,6]).
  * Writes radii [P] (int32) and *num_rendered (host).  Synchronises `stream`. */
-int sb_forward_geometry(const sb_settings* s, int P,
+SB_API int sb_forward_geometry(const sb_settings* s, int P,
                         const float* means3D, const float* opacities,
                         const float* scales, const float* rotations,
                         const float* cov3D_precomp,
@@ -97,7 +103,7 @@ int sb_forward_geometry(const sb_settings* s, int P,
  * duplicateWithKeys + SortPairs + identifyTileRanges + FORWARD::render
  * (X/cuda_rasterizer/rasterizer_impl.cu:284-337, forward.cu:261-393).
  * colors [P,3] (colors_precomp).  out_color [3,H,W], out_depth [1,H,W]. */
-int sb_forward_render(const sb_settings* s, int P, int num_rendered,
+SB_API int sb_forward_render(const sb_settings* s, int P, int num_rendered,
                       const float* colors,
                       const void* geom_ws, size_t geom_ws_bytes,
                       void* binning_ws, size_t binning_ws_bytes,
@@ -110,7 +116,7 @@ int sb_forward_render(const sb_settings* s, int P, int num_rendered,
  * dL_dout_color [3,H,W].  Outputs are fully overwritten (no pre-zeroing needed):
  * dL_dmeans3D [P,3], dL_dmeans2D [P,3], dL_dcolors [P,3], dL_dopacity [P],
  * dL_dscales [P,3], dL_drotations [P,4]; dL_dcov3D [P,6] may be NULL. */
-int sb_backward(const sb_settings* s, int P, int num_rendered,
+SB_API int sb_backward(const sb_settings* s, int P, int num_rendered,
                 const float* means3D, const float* colors,
                 const float* scales, const float* rotations,
                 const float* cov3D_precomp,
@@ -126,24 +132,33 @@ int sb_backward(const sb_settings* s, int P, int num_rendered,
                 void* stream);
 
 /* ---- markVisible (X/cuda_rasterizer/rasterizer_impl.cu:54-66,141-153) ------------------- */
-int sb_mark_visible(int P, const float* means3D, const float* viewmatrix,
+SB_API int sb_mark_visible(int P, const float* means3D, const float* viewmatrix,
                     const float* projmatrix, uint8_t* present, void* stream);
 
 /* ---- inspection (parity tests only): the intermediates the reference keeps in its
  *      geometry/binning/image byte buffers (X/cuda_rasterizer/rasterizer_impl.cu:155-194). ---
  * Any output pointer may be NULL.  All outputs are device pointers.
  *   depths [P] f32, means2D [P,2] f32, conic_opacity [P,4] f32, tiles_touched [P] u32 */
-int sb_export_geometry(int P, const void* geom_ws, size_t geom_ws_bytes,
+SB_API int sb_export_geometry(int P, const void* geom_ws, size_t geom_ws_bytes,
                        float* depths, float* means2D, float* conic_opacity,
                        uint32_t* tiles_touched, void* stream);
 /*   keys [R] u64 = (tile<<32)|depth_bits, point_list [R] u32, both in sorted order;
  *   ranges [tiles,2] u32, final_T [H*W] f32, n_contrib [H*W] u32 */
-int sb_export_binning(const sb_settings* s, int P, int num_rendered,
+SB_API int sb_export_binning(const sb_settings* s, int P, int num_rendered,
                       const void* geom_ws, size_t geom_ws_bytes,
                       const void* binning_ws, size_t binning_ws_bytes,
                       const void* image_ws, size_t image_ws_bytes,
                       uint64_t* keys, uint32_t* point_list, uint32_t* ranges,
                       float* final_T, uint32_t* n_contrib, void* stream);
+
+/* ---- per-stage device timing (measurement only; bench.py's roofline pass) -------------------
+ * Between sb_profile_begin() and sb_profile_end() every stage launch of this process is bracketed
+ * by CUDA events on its stream.  sb_profile_end synchronises, writes the summed milliseconds and call
+ * counts per stage (arrays of SB_NUM_STAGES) and disables the bracketing.  Not thread-safe. */
+#define SB_NUM_STAGES 10
+SB_API int sb_profile_begin(void);
+SB_API int sb_profile_end(float* stage_ms, int* stage_calls);
+SB_API const char* sb_stage_name(int stage);
 
 #ifdef __cplusplus
 }

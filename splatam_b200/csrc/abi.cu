@@ -3,6 +3,7 @@
 #include "common.cuh"
 #include <string.h>
 #include <stdio.h>
+#include <vector>
 
 namespace sb {
 
@@ -11,6 +12,20 @@ static thread_local char g_cuda_error[512] = "";
 void set_cuda_error(cudaError_t e, const char* where) {
     snprintf(g_cuda_error, sizeof(g_cuda_error), "%s: %s (%s)", where, cudaGetErrorName(e), cudaGetErrorString(e));
 }
+
+// ---- stage profiler ----
+struct StageRec { int stage; cudaEvent_t a, b; };
+static bool g_prof_on = false;
+static std::vector<StageRec> g_prof;
+ScopedStage::ScopedStage(int stage, cudaStream_t s) : slot(-1), st(s) {
+    if (!g_prof_on) return;
+    StageRec r; r.stage = stage;
+    if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
+    cudaEventRecord(r.a, st);
+    g_prof.push_back(r);
+    slot = (int)g_prof.size() - 1;
+}
+ScopedStage::~ScopedStage() { if (slot >= 0) cudaEventRecord(g_prof[slot].b, st); }
 
 GeometryWs carve_geometry(void* ws, int P, size_t* total) {
     Carver c(ws);
@@ -97,9 +112,9 @@ using namespace sb;
 
 extern "C" {
 
-int sb_abi_version(void) { return SB_ABI_VERSION; }
+SB_API int sb_abi_version(void) { return SB_ABI_VERSION; }
 
-const char* sb_status_string(int status) {
+SB_API const char* sb_status_string(int status) {
     switch (status) {
         case SB_OK: return "SB_OK";
         case SB_ERR_BAD_ARG: return "SB_ERR_BAD_ARG";
@@ -110,31 +125,31 @@ const char* sb_status_string(int status) {
     }
 }
 
-const char* sb_last_cuda_error(void) { return g_cuda_error; }
+SB_API const char* sb_last_cuda_error(void) { return g_cuda_error; }
 
-int sb_geometry_workspace_bytes(int P, size_t* bytes) {
+SB_API int sb_geometry_workspace_bytes(int P, size_t* bytes) {
     if (P < 0 || !bytes) return SB_ERR_BAD_ARG;
     carve_geometry(nullptr, P, bytes);
     return SB_OK;
 }
-int sb_image_workspace_bytes(int width, int height, size_t* bytes) {
+SB_API int sb_image_workspace_bytes(int width, int height, size_t* bytes) {
     if (width <= 0 || height <= 0 || !bytes) return SB_ERR_BAD_ARG;
     carve_image(nullptr, width, height, bytes);
     return SB_OK;
 }
-int sb_binning_workspace_bytes(int num_rendered, int width, int height, size_t* bytes) {
+SB_API int sb_binning_workspace_bytes(int num_rendered, int width, int height, size_t* bytes) {
     if (num_rendered < 0 || width <= 0 || height <= 0 || !bytes) return SB_ERR_BAD_ARG;
     const int tiles = ((width + kTile - 1) / kTile) * ((height + kTile - 1) / kTile);
     carve_binning(nullptr, num_rendered, tiles, bytes);
     return SB_OK;
 }
-int sb_backward_workspace_bytes(int P, size_t* bytes) {
+SB_API int sb_backward_workspace_bytes(int P, size_t* bytes) {
     if (P < 0 || !bytes) return SB_ERR_BAD_ARG;
     *bytes = ((size_t)(P > 0 ? P : 1) * kAccumStride * sizeof(float) + kAlign - 1) / kAlign * kAlign;
     return SB_OK;
 }
 
-int sb_forward_geometry(const sb_settings* s, int P, const float* means3D, const float* opacities,
+SB_API int sb_forward_geometry(const sb_settings* s, int P, const float* means3D, const float* opacities,
                         const float* scales, const float* rotations, const float* cov3D_precomp,
                         int32_t* radii, void* geom_ws, size_t geom_ws_bytes, int* num_rendered, void* stream) {
     if (!settings_ok(s) || P < 0 || !num_rendered) return SB_ERR_BAD_ARG;
@@ -159,7 +174,7 @@ int sb_forward_geometry(const sb_settings* s, int P, const float* means3D, const
     return SB_OK;
 }
 
-int sb_forward_render(const sb_settings* s, int P, int num_rendered, const float* colors,
+SB_API int sb_forward_render(const sb_settings* s, int P, int num_rendered, const float* colors,
                       const void* geom_ws, size_t geom_ws_bytes, void* binning_ws, size_t binning_ws_bytes,
                       void* image_ws, size_t image_ws_bytes, float* out_color, float* out_depth, void* stream) {
     if (!settings_ok(s) || P < 0 || num_rendered < 0 || !image_ws || !out_color || !out_depth) return SB_ERR_BAD_ARG;
@@ -178,7 +193,7 @@ int sb_forward_render(const sb_settings* s, int P, int num_rendered, const float
     return launch_blend_forward(*s, num_rendered, g, b, img, out_color, out_depth, st);
 }
 
-int sb_backward(const sb_settings* s, int P, int num_rendered, const float* means3D, const float* colors,
+SB_API int sb_backward(const sb_settings* s, int P, int num_rendered, const float* means3D, const float* colors,
                 const float* scales, const float* rotations, const float* cov3D_precomp, const int32_t* radii,
                 const void* geom_ws, size_t geom_ws_bytes, const void* binning_ws, size_t binning_ws_bytes,
                 const void* image_ws, size_t image_ws_bytes, void* bwd_ws, size_t bwd_ws_bytes,
@@ -201,7 +216,8 @@ int sb_backward(const sb_settings* s, int P, int num_rendered, const float* mean
     if (bwd_ws_bytes < need) return SB_ERR_WORKSPACE;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     float* accum = static_cast<float*>(bwd_ws);
-    SB_CUDA_CHECK(cudaMemsetAsync(accum, 0, (size_t)P * kAccumStride * sizeof(float), st));
+    { ScopedStage _p(kStAccumZero, st);
+      SB_CUDA_CHECK(cudaMemsetAsync(accum, 0, (size_t)P * kAccumStride * sizeof(float), st)); }
     int rc = launch_blend_backward(*s, num_rendered, b, img, dL_dout_color, accum, st);
     if (rc != SB_OK) return rc;
     return launch_geometry_backward(*s, P, means3D, colors, scales, rotations, cov3D_precomp, radii, accum,
@@ -209,7 +225,7 @@ int sb_backward(const sb_settings* s, int P, int num_rendered, const float* mean
                                     dL_drotations, dL_dcov3D, st);
 }
 
-int sb_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,
+SB_API int sb_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,
                     uint8_t* present, void* stream) {
     (void)projmatrix;  // the reference's test only uses the view matrix (auxiliary.h:154)
     if (P < 0) return SB_ERR_BAD_ARG;
@@ -218,7 +234,7 @@ int sb_mark_visible(int P, const float* means3D, const float* viewmatrix, const 
     return launch_mark_visible(P, means3D, viewmatrix, present, static_cast<cudaStream_t>(stream));
 }
 
-int sb_export_geometry(int P, const void* geom_ws, size_t geom_ws_bytes, float* depths, float* means2D,
+SB_API int sb_export_geometry(int P, const void* geom_ws, size_t geom_ws_bytes, float* depths, float* means2D,
                        float* conic_opacity, uint32_t* tiles_touched, void* stream) {
     if (P <= 0 || !geom_ws) return SB_ERR_BAD_ARG;
     size_t need = 0;
@@ -230,7 +246,7 @@ int sb_export_geometry(int P, const void* geom_ws, size_t geom_ws_bytes, float* 
     return SB_OK;
 }
 
-int sb_export_binning(const sb_settings* s, int P, int num_rendered, const void* geom_ws, size_t geom_ws_bytes,
+SB_API int sb_export_binning(const sb_settings* s, int P, int num_rendered, const void* geom_ws, size_t geom_ws_bytes,
                       const void* binning_ws, size_t binning_ws_bytes, const void* image_ws,
                       size_t image_ws_bytes, uint64_t* keys, uint32_t* point_list, uint32_t* ranges,
                       float* final_T, uint32_t* n_contrib, void* stream) {
@@ -259,6 +275,34 @@ int sb_export_binning(const sb_settings* s, int P, int num_rendered, const void*
     if (final_T) SB_CUDA_CHECK(cudaMemcpyAsync(final_T, img.final_T, sizeof(float) * hw, cudaMemcpyDeviceToDevice, st));
     if (n_contrib) SB_CUDA_CHECK(cudaMemcpyAsync(n_contrib, img.n_contrib, sizeof(uint32_t) * hw, cudaMemcpyDeviceToDevice, st));
     return SB_OK;
+}
+
+SB_API int sb_profile_begin(void) {
+    for (auto& r : g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    g_prof.clear();
+    g_prof_on = true;
+    return SB_OK;
+}
+
+SB_API int sb_profile_end(float* stage_ms, int* stage_calls) {
+    g_prof_on = false;
+    if (!stage_ms || !stage_calls) return SB_ERR_BAD_ARG;
+    for (int i = 0; i < kNumStages; ++i) { stage_ms[i] = 0.f; stage_calls[i] = 0; }
+    SB_CUDA_CHECK(cudaDeviceSynchronize());
+    for (auto& r : g_prof) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) { stage_ms[r.stage] += ms; stage_calls[r.stage]++; }
+        cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+    }
+    g_prof.clear();
+    return SB_OK;
+}
+
+SB_API const char* sb_stage_name(int stage) {
+    static const char* names[kNumStages] = {"project", "depth_sort", "depth_scan", "emit_instances", "tile_sort",
+                                            "ranges_records", "blend_forward", "accum_zero", "blend_backward",
+                                            "geometry_backward"};
+    return (stage >= 0 && stage < kNumStages) ? names[stage] : "?";
 }
 
 }  // extern "C"

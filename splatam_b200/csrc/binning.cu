@@ -66,12 +66,16 @@ int run_binning(const sb_settings& s, int P, int R, int bits, const float* color
     const uint32_t gx = (s.image_width + kTile - 1) / kTile;
     KeyT* tile_unsorted = reinterpret_cast<KeyT*>(b.tile_unsorted);
     KeyT* tile_sorted = reinterpret_cast<KeyT*>(b.tile_sorted);
+    { ScopedStage _p(kStEmit, st);
     emit_instances_kernel<KeyT><<<(P + 255) / 256, 256, 0, st>>>(P, g.sorted_idx, g.offsets, g.tiles_touched,
                                                                  g.rect, gx, tile_unsorted, b.val_unsorted);
+    }
     SB_LAUNCH_CHECK("emit_instances_kernel");
     size_t tb = b.cub_temp_bytes;
-    SB_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(b.cub_temp, tb, tile_unsorted, tile_sorted, b.val_unsorted,
-                                                  b.point_list, R, 0, bits, st));
+    { ScopedStage _p(kStTileSort, st);
+      SB_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(b.cub_temp, tb, tile_unsorted, tile_sorted, b.val_unsorted,
+                                                    b.point_list, R, 0, bits, st)); }
+    ScopedStage _p(kStRecords, st);
     ranges_and_records_kernel<KeyT><<<(R + 255) / 256, 256, 0, st>>>(R, tile_sorted, b.point_list, g.geomA,
                                                                      g.geomB, colors, img.ranges, b.recA,
                                                                      b.recB, b.recC);

@@ -196,6 +196,7 @@ int launch_blend_backward(const sb_settings& s, int R, const BinningWs& b, const
     if (R <= 0) return SB_OK;
     const int W = s.image_width, H = s.image_height;
     const uint32_t gx = (W + kTile - 1) / kTile, gy = (H + kTile - 1) / kTile;
+    ScopedStage _p(kStBlendBwd, st);
     blend_backward_kernel<<<gx * gy, kBlendThreads, 0, st>>>(img.ranges, b.recA, b.recB, b.recC, W, H, gx,
                                                              s.bg, img.final_T, img.n_contrib,
                                                              dL_dout_color, accum);

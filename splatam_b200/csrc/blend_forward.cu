@@ -152,6 +152,7 @@ int launch_blend_forward(const sb_settings& s, int R, const GeometryWs& g, const
     (void)R;
     const int W = s.image_width, H = s.image_height;
     const uint32_t gx = (W + kTile - 1) / kTile, gy = (H + kTile - 1) / kTile;
+    ScopedStage _p(kStBlendFwd, st);
     blend_forward_kernel<<<gx * gy, kBlendThreads, 0, st>>>(img.ranges, b.recA, b.recB, b.recC, g.depth_key,
                                                             W, H, gx, s.bg, out_color, out_depth,
                                                             img.final_T, img.n_contrib);

@@ -25,6 +25,15 @@ void set_cuda_error(cudaError_t e, const char* where);
         if (_e != cudaSuccess) { ::sb::set_cuda_error(_e, name); return SB_ERR_CUDA; } \
     } while (0)
 
+// ---- optional per-stage device timing (sb_profile_begin/end; used by bench.py's roofline pass) ----
+enum Stage { kStProject = 0, kStDepthSort, kStDepthScan, kStEmit, kStTileSort, kStRecords, kStBlendFwd,
+             kStAccumZero, kStBlendBwd, kStGeomBwd, kNumStages };
+struct ScopedStage {
+    int slot; cudaStream_t st;
+    ScopedStage(int stage, cudaStream_t s);
+    ~ScopedStage();
+};
+
 // ---- bump allocator over a caller-owned workspace --------------------------------------
 struct Carver {
     char* base; size_t off;

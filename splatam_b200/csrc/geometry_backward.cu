@@ -185,6 +185,7 @@ int launch_geometry_backward(const sb_settings& s, int P, const float* means3D, 
                              float* dL_dopacity, float* dL_dscales, float* dL_drotations,
                              float* dL_dcov3D, cudaStream_t st) {
     const float focal_y = s.image_height / (2.0f * s.tanfovy), focal_x = s.image_width / (2.0f * s.tanfovx);
+    ScopedStage _p(kStGeomBwd, st);
     geometry_backward_kernel<<<(P + 255) / 256, 256, 0, st>>>(
         P, means3D, colors, scales, rotations, cov3D_precomp, radii, s.viewmatrix, s.projmatrix, focal_x,
         focal_y, s.tanfovx, s.tanfovy, s.scale_modifier, accum, dL_dmeans3D, dL_dmeans2D, dL_dcolors,

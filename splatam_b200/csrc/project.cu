@@ -272,6 +272,7 @@ int launch_project(const sb_settings& s, int P, const float* means3D, const floa
     const float focal_y = H / (2.0f * s.tanfovy), focal_x = W / (2.0f * s.tanfovx);  // rasterizer_impl.cu:222-223
     const uint32_t gx = (W + kTile - 1) / kTile, gy = (H + kTile - 1) / kTile;
     auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+    ScopedStage _p(kStProject, st);
     project_kernel<<<(P + kProjThreads - 1) / kProjThreads, kProjThreads, 0, st>>>(
         P, means3D, opacities, scales, reinterpret_cast<const float4*>(rotations), cov3D_precomp,
         s.viewmatrix, s.projmatrix, W, H, s.tanfovx, s.tanfovy, focal_x, focal_y, s.scale_modifier,
@@ -287,12 +288,14 @@ int launch_project(const sb_settings& s, int P, const float* means3D, const floa
 // (ties in the reference resolve by emission order == Gaussian index).
 int launch_depth_order(int P, const GeometryWs& g, cudaStream_t st) {
     size_t tb = g.cub_temp_bytes;
-    SB_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(g.cub_temp, tb, g.depth_key, g.sorted_key, g.iota,
-                                                  g.sorted_idx, P, 0, 32, st));
+    { ScopedStage _p(kStDepthSort, st);
+      SB_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(g.cub_temp, tb, g.depth_key, g.sorted_key, g.iota,
+                                                    g.sorted_idx, P, 0, 32, st)); }
     TilesInDepthOrder op{g.tiles_touched, g.sorted_idx};
     cub::TransformInputIterator<uint32_t, TilesInDepthOrder, cub::CountingInputIterator<uint32_t>> it(
         cub::CountingInputIterator<uint32_t>(0u), op);
     tb = g.cub_temp_bytes;
+    ScopedStage _p(kStDepthScan, st);
     SB_CUDA_CHECK(cub::DeviceScan::InclusiveSum(g.cub_temp, tb, it, g.offsets, P, st));
     return SB_OK;
 }

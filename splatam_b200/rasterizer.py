@@ -1,0 +1,244 @@
+"""Host-side mirror of the reference operator API.
+
+Same names, kwargs, return tuple and error behaviour as
+``diff_gaussian_rasterization`` (reference: X/diff_gaussian_rasterization/__init__.py:17-196), but
+every stage runs in the hand-written sm_100a kernels behind ``libsplatam_b200.so``; torch is only
+used for device memory, the current stream and autograd bookkeeping.
+"""
+import ctypes
+from typing import NamedTuple
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+
+class GaussianRasterizationSettings(NamedTuple):
+    # field-for-field the reference's NamedTuple (__init__.py:134-145)
+    image_height: int
+    image_width: int
+    tanfovx: float
+    tanfovy: float
+    bg: torch.Tensor
+    scale_modifier: float
+    viewmatrix: torch.Tensor
+    projmatrix: torch.Tensor
+    sh_degree: int
+    campos: torch.Tensor
+    prefiltered: bool
+
+
+def _ptr(t):
+    """Device pointer, or NULL for the reference's "not provided" empty tensor (__init__.py:173-183)."""
+    if t is None or t.numel() == 0:
+        return None
+    return t.data_ptr()
+
+
+def _f32c(t, name):
+    if t is None or t.numel() == 0:
+        return t
+    if not t.is_cuda:
+        raise _lib.SplatamB200Error(f"{name} must be a CUDA tensor (there is no CPU fallback)")
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+class _SettingsPack:
+    """sb_settings plus the tensors that keep its device pointers alive."""
+
+    def __init__(self, rs: GaussianRasterizationSettings, device):
+        self.bg = _f32c(rs.bg.to(device), "bg")
+        self.view = _f32c(rs.viewmatrix.to(device), "viewmatrix")
+        self.proj = _f32c(rs.projmatrix.to(device), "projmatrix")
+        self.campos = _f32c(rs.campos.to(device), "campos") if rs.campos is not None else None
+        self.c = _lib.SbSettings(
+            int(rs.image_height), int(rs.image_width), float(rs.tanfovx), float(rs.tanfovy),
+            self.bg.data_ptr(), float(rs.scale_modifier), self.view.data_ptr(), self.proj.data_ptr(),
+            int(rs.sh_degree), _ptr(self.campos), int(bool(rs.prefiltered)))
+
+
+def _ws(nbytes, device):
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
+def _stream(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+class _State:
+    """Scratch kept alive between forward and backward (the reference saves its three byte buffers
+    on the autograd ctx, __init__.py:82-84)."""
+    __slots__ = ("geom", "binning", "image", "num_rendered", "settings")
+
+
+def _forward_impl(means3D, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, raster_settings):
+    lib = _lib.load()
+    if means3D.dim() != 2 or means3D.shape[1] != 3:
+        # rasterize_points.cu:56-58
+        raise _lib.SplatamB200Error("means3D must have dimensions (num_points, 3)")
+    device = means3D.device
+    if not means3D.is_cuda:
+        raise _lib.SplatamB200Error("means3D must be a CUDA tensor (there is no CPU fallback)")
+    P = means3D.shape[0]
+    H, W = int(raster_settings.image_height), int(raster_settings.image_width)
+    means3D = _f32c(means3D, "means3D")
+    colors_precomp = _f32c(colors_precomp, "colors_precomp")
+    opacities = _f32c(opacities, "opacities")
+    scales = _f32c(scales, "scales")
+    rotations = _f32c(rotations, "rotations")
+    cov3Ds_precomp = _f32c(cov3Ds_precomp, "cov3D_precomp")
+
+    with torch.cuda.device(device):
+        pack = _SettingsPack(raster_settings, device)
+        st = _stream(device)
+        color = torch.empty((3, H, W), dtype=torch.float32, device=device)
+        depth = torch.empty((1, H, W), dtype=torch.float32, device=device)
+        radii = torch.empty((P,), dtype=torch.int32, device=device)
+        state = _State()
+        state.settings = pack
+        n = ctypes.c_size_t(0)
+        _lib.check(lib.sb_geometry_workspace_bytes(P, ctypes.byref(n)), "sb_geometry_workspace_bytes")
+        state.geom = _ws(n.value, device)
+        _lib.check(lib.sb_image_workspace_bytes(W, H, ctypes.byref(n)), "sb_image_workspace_bytes")
+        state.image = _ws(n.value, device)
+        R = ctypes.c_int(0)
+        _lib.check(lib.sb_forward_geometry(
+            ctypes.byref(pack.c), P, _ptr(means3D), _ptr(opacities), _ptr(scales), _ptr(rotations),
+            _ptr(cov3Ds_precomp), _ptr(radii), state.geom.data_ptr(), state.geom.numel(),
+            ctypes.byref(R), st), "sb_forward_geometry")
+        state.num_rendered = R.value
+        _lib.check(lib.sb_binning_workspace_bytes(R.value, W, H, ctypes.byref(n)), "sb_binning_workspace_bytes")
+        state.binning = _ws(n.value, device)
+        _lib.check(lib.sb_forward_render(
+            ctypes.byref(pack.c), P, R.value, _ptr(colors_precomp), state.geom.data_ptr(), state.geom.numel(),
+            state.binning.data_ptr(), state.binning.numel(), state.image.data_ptr(), state.image.numel(),
+            color.data_ptr(), depth.data_ptr(), st), "sb_forward_render")
+    return color, radii, depth, state, (means3D, colors_precomp, scales, rotations, cov3Ds_precomp)
+
+
+def _backward_impl(state, saved, radii, grad_out_color):
+    lib = _lib.load()
+    means3D, colors_precomp, scales, rotations, cov3Ds_precomp = saved
+    device = means3D.device
+    P = means3D.shape[0]
+    pack = state.settings
+    grad_out_color = _f32c(grad_out_color, "grad_out_color")
+    with torch.cuda.device(device):
+        e = lambda *shape: torch.empty(shape, dtype=torch.float32, device=device)
+        g_means3D, g_means2D, g_colors, g_opac = e(P, 3), e(P, 3), e(P, 3), e(P, 1)
+        have_sr = scales is not None and scales.numel() != 0
+        g_scales = e(P, 3) if have_sr else torch.zeros((P, 3), dtype=torch.float32, device=device)
+        g_rot = e(P, 4) if have_sr else torch.zeros((P, 4), dtype=torch.float32, device=device)
+        g_cov3D = e(P, 6)
+        n = ctypes.c_size_t(0)
+        _lib.check(lib.sb_backward_workspace_bytes(P, ctypes.byref(n)), "sb_backward_workspace_bytes")
+        bwd_ws = _ws(n.value, device)
+        _lib.check(lib.sb_backward(
+            ctypes.byref(pack.c), P, state.num_rendered, _ptr(means3D), _ptr(colors_precomp), _ptr(scales),
+            _ptr(rotations), _ptr(cov3Ds_precomp), _ptr(radii),
+            state.geom.data_ptr(), state.geom.numel(), state.binning.data_ptr(), state.binning.numel(),
+            state.image.data_ptr(), state.image.numel(), bwd_ws.data_ptr(), bwd_ws.numel(),
+            _ptr(grad_out_color), _ptr(g_means3D), _ptr(g_means2D), _ptr(g_colors), _ptr(g_opac),
+            _ptr(g_scales) if have_sr else None, _ptr(g_rot) if have_sr else None, _ptr(g_cov3D),
+            _stream(device)), "sb_backward")
+    return g_means3D, g_means2D, g_colors, g_opac, g_scales, g_rot, g_cov3D
+
+
+class _RasterizeGaussians(torch.autograd.Function):
+    """autograd node with the reference's argument order and gradient tuple (__init__.py:40-132)."""
+
+    @staticmethod
+    def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
+                raster_settings):
+        if sh is not None and sh.numel() != 0:
+            raise _lib.SplatamB200Error(
+                "spherical-harmonics colours are not built yet (SB_ERR_UNSUPPORTED); "
+                "SplaTAM always passes colors_precomp (utils/slam_helpers.py:131-138)")
+        if P_is_zero(means3D):
+            H, W = int(raster_settings.image_height), int(raster_settings.image_width)
+            dev = means3D.device
+            ctx.empty = True
+            ctx.shapes = (means3D.shape, means2D.shape, colors_precomp.shape, opacities.shape, scales.shape,
+                          rotations.shape)
+            # rasterize_points.cu:67-75,81: P == 0 returns the zero-filled images without launching
+            return (torch.zeros((3, H, W), device=dev), torch.zeros((0,), dtype=torch.int32, device=dev),
+                    torch.zeros((1, H, W), device=dev))
+        color, radii, depth, state, saved = _forward_impl(
+            means3D, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, raster_settings)
+        ctx.empty = False
+        ctx.state = state
+        ctx.opac_shape = opacities.shape
+        ctx.save_for_backward(radii, *[t if t is not None else torch.empty(0) for t in saved])
+        ctx.mark_non_differentiable(radii, depth)
+        return color, radii, depth
+
+    @staticmethod
+    def backward(ctx, grad_out_color, _grad_radii, _grad_depth):
+        # depth carries no gradient (the reference drops it, __init__.py:88)
+        if ctx.empty:
+            z = [torch.zeros(s) for s in ctx.shapes]
+            return z[0], z[1], None, z[2], z[3], z[4], z[5], None, None
+        radii, *saved = ctx.saved_tensors
+        g_means3D, g_means2D, g_colors, g_opac, g_scales, g_rot, g_cov3D = _backward_impl(
+            ctx.state, saved, radii, grad_out_color)
+        needs_cov = saved[4].numel() != 0
+        return (g_means3D, g_means2D, None, g_colors, g_opac.reshape(ctx.opac_shape),
+                g_scales if not needs_cov else None, g_rot if not needs_cov else None,
+                g_cov3D if needs_cov else None, None)
+
+
+def P_is_zero(means3D):
+    return means3D.shape[0] == 0
+
+
+def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
+                        raster_settings):
+    return _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
+                                     cov3Ds_precomp, raster_settings)
+
+
+class GaussianRasterizer(nn.Module):
+    def __init__(self, raster_settings):
+        super().__init__()
+        self.raster_settings = raster_settings
+
+    def markVisible(self, positions):
+        """Boolean mask ``view_z > 0.2`` per point (reference __init__.py:152-161)."""
+        lib = _lib.load()
+        with torch.no_grad():
+            rs = self.raster_settings
+            pos = _f32c(positions, "positions")
+            P = pos.shape[0]
+            present = torch.zeros((P,), dtype=torch.bool, device=pos.device)
+            if P:
+                view = _f32c(rs.viewmatrix.to(pos.device), "viewmatrix")
+                proj = _f32c(rs.projmatrix.to(pos.device), "projmatrix")
+                with torch.cuda.device(pos.device):
+                    _lib.check(lib.sb_mark_visible(P, pos.data_ptr(), view.data_ptr(), proj.data_ptr(),
+                                                   present.data_ptr(), _stream(pos.device)), "sb_mark_visible")
+        return present
+
+    def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None,
+                cov3D_precomp=None):
+        raster_settings = self.raster_settings
+        # the two argument checks of the reference, same exception type and text (__init__.py:167-171)
+        if (shs is None and colors_precomp is None) or (shs is not None and colors_precomp is not None):
+            raise Exception('Please provide excatly one of either SHs or precomputed colors!')
+        if ((scales is None or rotations is None) and cov3D_precomp is None) or \
+                ((scales is not None or rotations is not None) and cov3D_precomp is not None):
+            raise Exception('Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!')
+        if shs is None:
+            shs = torch.Tensor([])
+        if colors_precomp is None:
+            colors_precomp = torch.Tensor([])
+        if scales is None:
+            scales = torch.Tensor([])
+        if rotations is None:
+            rotations = torch.Tensor([])
+        if cov3D_precomp is None:
+            cov3D_precomp = torch.Tensor([])
+        return rasterize_gaussians(means3D, means2D, shs, colors_precomp, opacities, scales, rotations,
+                                   cov3D_precomp, raster_settings)

@@ -1,0 +1,137 @@
+"""CPU suite: the C oracle against the independent float64 brute-force composite (autograd backward),
+its own invariants, and the committed golden vectors produced by the reference extension on a B200."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import scenes
+from oracle import bruteforce_torch as BF
+from oracle import oracle as O
+from util import GOLDEN, l2_rel, rel_err
+
+
+def _brute(scene, dtype=torch.float64, grad_seed=None):
+    inp = {k: v.clone().to(dtype).requires_grad_(grad_seed is not None) for k, v in dict(
+        means3D=scene.means3D, colors=scene.colors, opacities=scene.opacities, scales=scene.scales,
+        rotations=scene.rotations).items()}
+    m2 = torch.zeros(scene.P, 3, dtype=dtype, requires_grad=grad_seed is not None)
+    out = BF.render(inp["means3D"], inp["colors"], inp["opacities"], inp["scales"], inp["rotations"],
+                    width=scene.w, height=scene.h, tanfovx=scene.tanfovx, tanfovy=scene.tanfovy, bg=scene.bg,
+                    viewmatrix=scene.view[0], projmatrix=scene.proj[0], means2D=m2, dtype=dtype)
+    grads = None
+    if grad_seed is not None:
+        g = torch.Generator().manual_seed(grad_seed)
+        dL = torch.randn(3, scene.h, scene.w, generator=g)
+        (out["color"] * dL.to(dtype)).sum().backward()
+        grads = dict(means3D=inp["means3D"].grad, means2D=m2.grad, colors=inp["colors"].grad,
+                     opacities=inp["opacities"].grad, scales=inp["scales"].grad, rotations=inp["rotations"].grad)
+        grads = {k: v.numpy() for k, v in grads.items()}
+        grads["dL"] = dL.numpy()
+    return out, grads
+
+
+@pytest.mark.parametrize("make", [scenes.config1, scenes.edge_cases, lambda: scenes.dense_opaque(P=600, w=64, h=48)])
+def test_oracle_forward_matches_bruteforce(make):
+    sc = make()
+    o = sc.oracle()
+    r = o.render()
+    bf, _ = _brute(sc)
+    geo = o.geometry()
+    assert np.array_equal(geo["radii"], bf["radii"].numpy()), "radii (int) must agree with the float64 restatement"
+    col = bf["color"].numpy()
+    bad = np.abs(r["color"] - col) > 2e-5
+    # a pair within an ulp of a threshold may flip between float32 and float64: allow a handful of pixels
+    assert bad.mean() < 2e-3, f"colour mismatch fraction {bad.mean()}"
+    assert np.median(np.abs(r["color"] - col)) < 1e-6
+    assert (np.abs(r["final_T"] - bf["final_T"].numpy()) > 2e-5).mean() < 2e-3
+    assert (r["n_contrib"] != bf["n_contrib"].numpy()).mean() < 2e-3
+    assert (np.abs(r["depth"] - bf["depth"].numpy()) > 1e-5).mean() < 5e-3
+
+
+@pytest.mark.parametrize("make", [scenes.config1, scenes.edge_cases])
+def test_oracle_backward_matches_autograd(make):
+    sc = make()
+    o = sc.oracle()
+    o.render()
+    _, gbf = _brute(sc, grad_seed=3)
+    g = o.backward(gbf["dL"])
+    for k in ["means3D", "means2D", "colors", "opacities", "scales", "rotations"]:
+        a, b = g[k].reshape(-1), gbf[k].reshape(-1)
+        assert l2_rel(a, b) < 2e-3, (k, l2_rel(a, b))
+        frac_bad = (rel_err(a, b, floor_frac=1e-4) > 1e-2).mean()
+        assert frac_bad < 0.02, (k, frac_bad)
+
+
+def test_oracle_binning_invariants():
+    sc = scenes.edge_cases()
+    o = sc.oracle()
+    b, geo = o.binning(), o.geometry()
+    keys, lst, ranges = b["keys"], b["point_list"], b["ranges"]
+    assert o.R == int(geo["tiles_touched"].sum())
+    assert np.all(keys[1:] >= keys[:-1]), "keys ascending"
+    # ties resolve by Gaussian index (stable sort of an index-ordered emission)
+    same = keys[1:] == keys[:-1]
+    assert np.all(lst[1:][same] > lst[:-1][same])
+    # key low word == depth bits of the listed Gaussian; culled Gaussians never appear
+    assert np.array_equal((keys & 0xFFFFFFFF).astype(np.uint32), geo["depths"].view(np.uint32)[lst])
+    assert np.all(geo["radii"][lst] > 0)
+    tile = (keys >> 32).astype(np.int64)
+    for t in range(ranges.shape[0]):
+        lo, hi = ranges[t]
+        assert np.all(tile[lo:hi] == t)
+    assert int((ranges[:, 1] - ranges[:, 0]).sum()) == o.R
+
+
+def test_oracle_mark_visible_and_empty():
+    sc = scenes.edge_cases()
+    vis = O.mark_visible(sc.oracle_cam(), sc.means3D.numpy())
+    z = (torch.cat([sc.means3D, torch.ones(sc.P, 1)], 1) @ sc.view[0])[:, 2].numpy()
+    assert np.array_equal(vis, ~(z <= 0.2))
+    empty = scenes.Scene("empty", 32, 32, 30., 30., 15.5, 15.5, torch.zeros(0, 3), torch.zeros(0, 3), torch.zeros(0),
+                         torch.zeros(0, 3), torch.zeros(0, 4), bg=(0.1, 0.2, 0.3))
+    r = empty.oracle().render()
+    assert np.allclose(r["color"][0], 0.1) and np.allclose(r["depth"], 15.0) and r["n_contrib"].max() == 0
+
+
+def _golden_files():
+    return sorted(glob.glob(os.path.join(GOLDEN, "*.npz")))
+
+
+@pytest.mark.parametrize("path", _golden_files() or [None])
+def test_oracle_matches_reference_golden(path):
+    """Golden vectors = outputs of the UNMODIFIED reference extension run on a B200
+    (tests/golden/make_golden.py).  This is what pins the oracle."""
+    if path is None:
+        pytest.skip("no golden fixtures committed yet")
+    z = np.load(path)
+    sc = scenes.Scene(str(z["name"]), int(z["w"]), int(z["h"]), float(z["fx"]), float(z["fy"]), float(z["cx"]),
+                      float(z["cy"]), torch.from_numpy(z["means3D"]), torch.from_numpy(z["colors"]),
+                      torch.from_numpy(z["opacities"]), torch.from_numpy(z["scales"]), torch.from_numpy(z["rotations"]),
+                      w2c=torch.from_numpy(z["w2c"]), bg=tuple(z["bg"].tolist()))
+    assert np.array_equal(sc.view.numpy().reshape(-1), z["viewmatrix"].reshape(-1))
+    assert np.array_equal(sc.proj.numpy().reshape(-1), z["projmatrix"].reshape(-1))
+    o = sc.oracle()
+    geo, b = o.geometry(), o.binning()
+    # integer / bit-exact quantities
+    assert np.array_equal(geo["radii"], z["ref_radii"])
+    vis = z["ref_radii"] > 0
+    assert np.array_equal(geo["tiles_touched"], z["ref_tiles_touched"])
+    assert np.array_equal(geo["depths"][vis].view(np.uint32), z["ref_depths"][vis].view(np.uint32))
+    assert np.array_equal(geo["means2D"][vis].view(np.uint32), z["ref_means2D"][vis].view(np.uint32))
+    assert np.array_equal(geo["conic_opacity"][vis].view(np.uint32), z["ref_conic_opacity"][vis].view(np.uint32))
+    assert np.array_equal(geo["cov3D"].view(np.uint32), z["ref_cov3D"].view(np.uint32))
+    assert np.array_equal(b["keys"], z["ref_keys"]) and np.array_equal(b["point_list"], z["ref_point_list"])
+    assert np.array_equal(b["ranges"], z["ref_ranges"])
+    # float quantities (CPU expf vs libdevice expf)
+    r = o.render()
+    assert (r["n_contrib"] != z["ref_n_contrib"]).mean() < 1e-3
+    assert (rel_err(r["color"], z["ref_color"], 1e-3) > 1e-4).mean() < 1e-3
+    assert (rel_err(r["final_T"], z["ref_final_T"], 1e-3) > 1e-4).mean() < 1e-3
+    assert (np.abs(r["depth"] - z["ref_depth"]) > 0).mean() < 1e-3
+    g = o.backward(z["dL_dcolor"])
+    for k in ["means3D", "means2D", "colors", "opacities", "scales", "rotations"]:
+        ref = z["ref_grad_" + k].reshape(-1)
+        assert l2_rel(g[k].reshape(-1), ref) < 1e-4, (k, l2_rel(g[k].reshape(-1), ref))
