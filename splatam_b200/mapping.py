@@ -1,0 +1,205 @@
+"""Keyframe-sharded mapping step -- NEW functionality; the reference mapping
+loop is single-GPU and renders ONE keyframe per Adam step (R/scripts/splatam.py:828-885).
+
+One process per GPU.  Every rank holds the full Gaussian parameter set; in a K-rank step rank r
+renders keyframe ``perm[step*K + r]`` of the selected window (2 raster calls, RGB and
+depth/silhouette, exactly SplaTAM's ``get_loss(mapping=True)``: R/scripts/splatam.py:214-347), the
+per-Gaussian gradients of all ranks are summed with ONE all-reduce over a flat, packed gradient
+bucket (NCCL over NVLink on the box, gloo in the CPU tests), and every rank applies the same Adam
+update so the replicas stay bit-identical without any parameter broadcast.  Tracking stays
+single-GPU.  A K-rank step is a K-keyframe minibatch: gradients equal a 1-process accumulation over
+the same K keyframes up to float summation order (tests/test_mapping_gloo.py).
+
+The PyTorch glue below restates R/utils/slam_helpers.py:124-139,196-304 and
+R/utils/slam_external.py:25-97 (transform_to_frame, rendervars, L1, SSIM); it is host-side plumbing
+around the operator, not part of the rasterizer hot path.
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+GAUSSIAN_KEYS = ("means3D", "rgb_colors", "unnorm_rotations", "logit_opacities", "log_scales")
+
+
+def build_rotation(q):
+    """Unit-quaternion (w,x,y,z) rows -> rotation matrices (R/utils/slam_external.py:25-42)."""
+    q = q / torch.sqrt((q * q).sum(-1, keepdim=True))
+    r, x, y, z = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
+    return torch.stack([1 - 2 * (y * y + z * z), 2 * (x * y - r * z), 2 * (x * z + r * y),
+                        2 * (x * y + r * z), 1 - 2 * (x * x + z * z), 2 * (y * z - r * x),
+                        2 * (x * z - r * y), 2 * (y * z + r * x), 1 - 2 * (x * x + y * y)], -1).reshape(-1, 3, 3)
+
+
+def quat_mult(q1, q2):
+    """Hamilton product, (w,x,y,z) convention (R/utils/slam_helpers.py:24-31)."""
+    w1, x1, y1, z1 = q1.T
+    w2, x2, y2, z2 = q2.T
+    return torch.stack([w1 * w2 - x1 * x2 - y1 * y2 - z1 * z2, w1 * x2 + x1 * w2 + y1 * z2 - z1 * y2,
+                        w1 * y2 - x1 * z2 + y1 * w2 + z1 * x2, w1 * z2 + x1 * y2 - y1 * x2 + z1 * w2]).T
+
+
+def transform_to_frame(params, time_idx, gaussians_grad, camera_grad):
+    """World -> camera-frame Gaussians for frame `time_idx` (R/utils/slam_helpers.py:252-304)."""
+    rot, tran = params["cam_unnorm_rots"][..., time_idx], params["cam_trans"][..., time_idx]
+    if not camera_grad:
+        rot, tran = rot.detach(), tran.detach()
+    cam_rot = F.normalize(rot)
+    dev = params["means3D"].device
+    rel_w2c = torch.eye(4, device=dev, dtype=torch.float32)
+    rel_w2c[:3, :3] = build_rotation(cam_rot)
+    rel_w2c[:3, 3] = tran
+    pts, unnorm = params["means3D"], params["unnorm_rotations"]
+    if not gaussians_grad:
+        pts, unnorm = pts.detach(), unnorm.detach()
+    pts4 = torch.cat((pts, torch.ones(pts.shape[0], 1, device=dev)), dim=1)
+    out = {"means3D": (rel_w2c @ pts4.T).T[:, :3]}
+    if params["log_scales"].shape[1] == 1:            # isotropic: rotations irrelevant
+        out["unnorm_rotations"] = unnorm
+    else:
+        out["unnorm_rotations"] = quat_mult(cam_rot, F.normalize(unnorm))
+    return out
+
+
+def _scales(params):
+    ls = params["log_scales"]
+    return torch.exp(torch.tile(ls, (1, 3)) if ls.shape[1] == 1 else ls)
+
+
+def rgb_rendervar(params, tg):
+    """R/utils/slam_helpers.py:124-139."""
+    return dict(means3D=tg["means3D"], colors_precomp=params["rgb_colors"],
+                rotations=F.normalize(tg["unnorm_rotations"]), opacities=torch.sigmoid(params["logit_opacities"]),
+                scales=_scales(params), means2D=torch.zeros_like(params["means3D"], requires_grad=True) + 0)
+
+
+def depth_sil_rendervar(params, w2c, tg):
+    """colours = [z, 1, z^2] in the camera frame (R/utils/slam_helpers.py:196-249)."""
+    pts = tg["means3D"]
+    pts4 = torch.cat((pts, torch.ones_like(pts[:, :1])), dim=-1)
+    z = (w2c @ pts4.T).T[:, 2:3]
+    col = torch.cat((z, torch.ones_like(z), z * z), dim=1)
+    return dict(means3D=pts, colors_precomp=col, rotations=F.normalize(tg["unnorm_rotations"]),
+                opacities=torch.sigmoid(params["logit_opacities"]), scales=_scales(params),
+                means2D=torch.zeros_like(params["means3D"], requires_grad=True) + 0)
+
+
+def _ssim_window(channel, device, size=11, sigma=1.5):
+    g = torch.tensor([math.exp(-(x - size // 2) ** 2 / float(2 * sigma ** 2)) for x in range(size)])
+    g = (g / g.sum()).unsqueeze(1)
+    return g.mm(g.t()).float()[None, None].expand(channel, 1, size, size).contiguous().to(device)
+
+
+def calc_ssim(img1, img2, window_size=11):
+    """R/utils/slam_external.py:66-97 (mean SSIM, 11x11 Gaussian window, sigma 1.5)."""
+    ch = img1.size(-3)
+    w = _ssim_window(ch, img1.device, window_size).type_as(img1)
+    pad = window_size // 2
+    conv = lambda t: F.conv2d(t, w, padding=pad, groups=ch)
+    mu1, mu2 = conv(img1), conv(img2)
+    mu1_sq, mu2_sq, mu12 = mu1.pow(2), mu2.pow(2), mu1 * mu2
+    s1, s2, s12 = conv(img1 * img1) - mu1_sq, conv(img2 * img2) - mu2_sq, conv(img1 * img2) - mu12
+    c1, c2 = 0.01 ** 2, 0.03 ** 2
+    return (((2 * mu12 + c1) * (2 * s12 + c2)) / ((mu1_sq + mu2_sq + c1) * (s1 + s2 + c2))).mean()
+
+
+def mapping_loss(params, frame, render, loss_weights=(0.5, 1.0), ignore_outlier_depth_loss=False):
+    """SplaTAM get_loss(mapping=True): Gaussians get gradient, camera does not
+    (R/scripts/splatam.py:214-347 with tracking=False, mapping=True, do_ba=False, use_l1=True).
+    frame: dict(im [3,H,W], depth [1,H,W], cam settings, w2c [4,4] first-frame w2c, id time index).
+    render(settings, **rendervar) -> (image, radii, depth)."""
+    tg = transform_to_frame(params, frame["id"], gaussians_grad=True, camera_grad=False)
+    im, radius, _ = render(frame["cam"], **rgb_rendervar(params, tg))
+    depth_sil, _, _ = render(frame["cam"], **depth_sil_rendervar(params, frame["w2c"], tg))
+    depth = depth_sil[0:1]
+    uncertainty = (depth_sil[2:3] - depth ** 2).detach()
+    mask = (frame["depth"] > 0) & (~torch.isnan(depth)) & (~torch.isnan(uncertainty))
+    if ignore_outlier_depth_loss:
+        err = torch.abs(frame["depth"] - depth) * (frame["depth"] > 0)
+        mask = mask & (err < 10 * err.median())
+    mask = mask.detach()
+    l_depth = torch.abs(frame["depth"] - depth)[mask].mean()
+    l_im = 0.8 * torch.abs(im - frame["im"]).mean() + 0.2 * (1.0 - calc_ssim(im, frame["im"]))
+    return loss_weights[0] * l_im + loss_weights[1] * l_depth, radius
+
+
+class FlatGaussians:
+    """The five Gaussian parameter tensors as views into ONE flat fp32 buffer, their gradients as
+    views into ONE flat gradient bucket of the same layout -- the packed send buffer of the
+    all-reduce (48-56 B per Gaussian)."""
+
+    def __init__(self, tensors):
+        self.shapes = {k: tuple(tensors[k].shape) for k in GAUSSIAN_KEYS}
+        n = sum(math.prod(s) for s in self.shapes.values())
+        dev = tensors["means3D"].device
+        self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.flat_grad = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.params, off = {}, 0
+        for k in GAUSSIAN_KEYS:
+            m = math.prod(self.shapes[k])
+            self.flat[off:off + m].copy_(tensors[k].detach().reshape(-1))
+            p = self.flat[off:off + m].view(self.shapes[k]).requires_grad_(True)
+            p.grad = self.flat_grad[off:off + m].view(self.shapes[k])   # autograd accumulates in place
+            self.params[k] = p
+            off += m
+
+    def zero_grad(self):
+        self.flat_grad.zero_()
+
+
+def default_render(settings, **rendervar):
+    from .rasterizer import GaussianRasterizer
+    return GaussianRasterizer(raster_settings=settings)(**rendervar)
+
+
+class ShardedMapper:
+    """Data-parallel mapping over keyframes.  `lrs` follow R/configs/replica/splatam.py:92-100."""
+
+    DEFAULT_LRS = dict(means3D=0.0001, rgb_colors=0.0025, unnorm_rotations=0.001, logit_opacities=0.05,
+                       log_scales=0.001)
+
+    def __init__(self, gaussians, cam_unnorm_rots, cam_trans, lrs=None, render=default_render, group=None, seed=0):
+        import torch.distributed as dist
+        self.dist = dist if (dist.is_available() and dist.is_initialized()) else None
+        self.group = group
+        self.rank = self.dist.get_rank(group) if self.dist else 0
+        self.world = self.dist.get_world_size(group) if self.dist else 1
+        self.g = FlatGaussians(gaussians)
+        self.cam = dict(cam_unnorm_rots=cam_unnorm_rots.detach(), cam_trans=cam_trans.detach())
+        lrs = dict(self.DEFAULT_LRS, **(lrs or {}))
+        self.opt = torch.optim.Adam([{"params": [self.g.params[k]], "name": k, "lr": lrs[k]} for k in GAUSSIAN_KEYS],
+                                    lr=0.0, eps=1e-15)
+        self.render = render
+        self.gen = torch.Generator().manual_seed(seed)   # shared seed -> identical schedule on every rank
+        self.step_idx = 0
+
+    def params(self):
+        return dict(self.g.params, **self.cam)
+
+    def schedule(self, window_size):
+        """Keyframe index (into the window) rendered by each rank this step: a shared-seed permutation
+        dealt round-robin, so ranks draw distinct keyframes whenever the window holds >= world frames."""
+        perm = torch.randperm(window_size, generator=self.gen).tolist()
+        return [perm[r % window_size] for r in range(self.world)]
+
+    def accumulate(self, frame):
+        """Local backward of one keyframe into the flat gradient bucket (no communication)."""
+        loss, radius = mapping_loss(self.params(), frame, self.render)
+        loss.backward()
+        return loss.detach(), radius
+
+    def step(self, window):
+        """One sharded mapping step over `window` (list of keyframe dicts).  Returns the mean loss."""
+        picks = self.schedule(len(window))
+        self.g.zero_grad()
+        loss, radius = self.accumulate(window[picks[self.rank]])
+        seen = (radius > 0).to(torch.int32)
+        if self.dist and self.world > 1:
+            self.dist.all_reduce(self.g.flat_grad, op=self.dist.ReduceOp.SUM, group=self.group)
+            self.dist.all_reduce(seen, op=self.dist.ReduceOp.MAX, group=self.group)
+            lt = loss.clone()
+            self.dist.all_reduce(lt, op=self.dist.ReduceOp.SUM, group=self.group)
+            loss = lt / self.world
+        self.opt.step()
+        self.step_idx += 1
+        return float(loss), seen.bool(), picks

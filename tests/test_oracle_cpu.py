@@ -122,7 +122,10 @@ def test_oracle_matches_reference_golden(path):
     assert np.array_equal(geo["depths"][vis].view(np.uint32), z["ref_depths"][vis].view(np.uint32))
     assert np.array_equal(geo["means2D"][vis].view(np.uint32), z["ref_means2D"][vis].view(np.uint32))
     assert np.array_equal(geo["conic_opacity"][vis].view(np.uint32), z["ref_conic_opacity"][vis].view(np.uint32))
-    assert np.array_equal(geo["cov3D"].view(np.uint32), z["ref_cov3D"].view(np.uint32))
+    # the reference writes cov3D only for points that pass the near-plane test (forward.cu:193-214);
+    # rows of culled points are uninitialised scratch memory there
+    front = O.mark_visible(sc.oracle_cam(), sc.means3D.numpy())
+    assert np.array_equal(geo["cov3D"][front].view(np.uint32), z["ref_cov3D"][front].view(np.uint32))
     assert np.array_equal(b["keys"], z["ref_keys"]) and np.array_equal(b["point_list"], z["ref_point_list"])
     assert np.array_equal(b["ranges"], z["ref_ranges"])
     # float quantities (CPU expf vs libdevice expf)

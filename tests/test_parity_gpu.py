@@ -123,6 +123,9 @@ def test_full_size_properties(cuda_device):
     c = run_ours(sc, dL1 + dL2, intermediates=False)
     assert np.array_equal(_bits(a["color"]), _bits(b["color"]))
     for k in GRADS:
+        if k == "rotations":   # isotropic scene: the quaternion gradient is pure cancellation noise (~1e-12)
+            assert np.abs(c["grad_" + k]).max() < 1e-6 * np.abs(c["grad_scales"]).max()
+            continue
         assert l2_rel(c["grad_" + k], a["grad_" + k] + b["grad_" + k]) < 1e-5, k
     # a zero upstream gradient gives exactly zero gradients; transmittance is in (0, 1]
     z = run_ours(sc, np.zeros_like(dL1), intermediates=False)
