@@ -40,6 +40,7 @@ def parse():
     ap.add_argument("--workload", default="config3", choices=["config3", "room50k", "tum3m", "config1"])
     ap.add_argument("--gaussians", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-mapping", action="store_true")
     return ap.parse_args()
 
 
@@ -196,6 +197,35 @@ def timed(step, steps, warmup, dev, dist_on):
     return ms
 
 
+def mapping_bench(dev, world, dist_on, impl, steps=8, warmup=3, P=1_000_000):
+    """Secondary BASELINE metric: mapping keyframe-iterations/sec.  One iteration = SplaTAM's
+    get_loss(mapping=True) (2 raster fwd + 2 raster bwd + glue) + one Adam step; a K-rank step renders K
+    keyframes (one per GPU), all-reduces the packed per-Gaussian gradient bucket over NCCL and applies the
+    same Adam update on every rank.  Synthetic Replica-sized room, isotropic Gaussians."""
+    from splatam_b200 import mapping as M
+    Rast, Settings = get_ops(impl)
+    sc = scenes.room(seed=4, P=P)
+    cam = sc.settings(Settings, dev)
+    g = torch.Generator().manual_seed(0)
+    gauss = dict(means3D=sc.means3D, rgb_colors=sc.colors, unnorm_rotations=sc.rotations,
+                 logit_opacities=torch.logit(sc.opacities.clamp(0.02, 0.98)), log_scales=torch.log(sc.scales[:, :1]))
+    gauss = {k: v.to(dev) for k, v in gauss.items()}
+    nframes = 8
+    rots = torch.zeros(1, 4, nframes); rots[:, 0] = 1.0
+    rots[:, 1:] = 0.005 * torch.randn(1, 3, nframes, generator=g)
+    trans = 0.02 * torch.randn(1, 3, nframes, generator=g)
+    frames = [dict(id=t, cam=cam, w2c=torch.eye(4, device=dev), im=torch.rand(3, sc.h, sc.w, generator=g).to(dev),
+                   depth=(1.0 + 2.0 * torch.rand(1, sc.h, sc.w, generator=g)).to(dev)) for t in range(nframes)]
+    render = (lambda settings, **rv: Rast(raster_settings=settings)(**rv))
+    mapper = M.ShardedMapper(gauss, rots.to(dev), trans.to(dev), render=render, seed=11)
+    ms = timed(lambda: mapper.step(frames), steps, warmup, dev, dist_on) / steps
+    return dict(metric="mapping keyframe-iters/sec", value=world * 1000.0 / ms, unit="keyframe-iters/s",
+                ms_per_step=ms, keyframes_per_step=world, gaussians=P, width=sc.w, height=sc.h,
+                allreduce_bytes=int(mapper.g.flat_grad.numel() * 4) if world > 1 else 0,
+                note="2 raster fwd + 2 bwd + PyTorch glue + Adam per keyframe; NCCL all-reduce of the packed "
+                     "gradient bucket when n_gpus > 1")
+
+
 def cpu_oracle_run(scene, budget_s=25.0):
     """Times the C oracle (fwd render OpenMP over tiles, backward single-threaded double accumulation)
     on a bounded sample: the same view with the first P_s Gaussians, P_s chosen so one fwd+bwd stays
@@ -325,6 +355,11 @@ def main():
                                                "CUB radix sort/scan launches and 2 memsets not counted")
         if rank == 0 and world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"], _, _ = cpu_oracle_run(scene)
+    if not args.no_mapping:
+        try:
+            line["mapping"] = mapping_bench(dev, world, dist_on, args.impl)
+        except Exception as e:  # never lose the headline line
+            line["mapping"] = {"error": repr(e)[:200]}
     if rank == 0:
         print(json.dumps(line))
     if dist_on:
