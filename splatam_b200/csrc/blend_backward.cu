@@ -1,15 +1,21 @@
 // blend_backward.cu -- backward of the alpha-composite (BACKWARD::renderCUDA,
 // X/cuda_rasterizer/backward.cu:399-557): walks every tile's sorted list back-to-front from the last
-// contributor, rebuilds T by division exactly as the reference does, and produces per-Gaussian
+// contributor, rebuilds T as the reference does (T /= 1-alpha), and produces per-Gaussian
 // dL/d{mean2D.xy, conic.xx/xy/yy, opacity, colour rgb}.
 //
-// Structure mirrors blend_forward.cu (TMA producer warp + 8 autonomous consumer warps, one 8x4
-// pixel rectangle each, warp-ballot culling with the same conservative boxes).  The reference issues
-// 9 global float atomics per contributing pixel-pair (backward.cu:523-554); here the 9 partial sums of
-// a (warp, Gaussian) pair are reduced across the 32 lanes with a value-splitting butterfly (12 shuffles
-// for 9 values: each xor step halves the number of values a lane still carries) and then written with
-// ONE reduction instruction whose 9 active lanes hit 9 consecutive floats of the Gaussian's 48-B
-// accumulator row -- 32x fewer L2 atomic operations.
+// Structure mirrors blend_forward.cu (TMA producer warp + 8 autonomous consumer warps, one 8x4 pixel
+// rectangle each, warp-ballot culling with the same conservative boxes).  The reference issues 9 global
+// float atomics per contributing pixel pair (backward.cu:523-554).  Here the reduction over pixels is
+// done in two phases per warp:
+//   phase 1 (lane = pixel, sequential along the list): per surviving Gaussian each lane computes only
+//     the two scalars that depend on the running per-pixel state, w = G*dL/dG and ca = alpha*T, and
+//     parks them in a 16-slot shared-memory queue [slot][pixel];
+//   phase 2 (lane = Gaussian, when 16 survivors are queued): two lanes per queued Gaussian sweep 16
+//     pixels each and accumulate the nine sums  S{w, w dx, w dy, w dx^2, w dx dy, w dy^2}, S ca*dL/dpix[rgb]
+//     in registers at full lane utilisation, combine with one xor-16 shuffle per sum, turn them into
+//     the reference's nine gradients and flush each with ONE reduction per quantity per (warp, Gaussian).
+// Phase 1 runs at the (low) lane utilisation the pixel footprint dictates but is short; the wide part of
+// the arithmetic runs in phase 2 with all 32 lanes busy.
 #include "common.cuh"
 #include "pipeline.cuh"
 
@@ -21,6 +27,8 @@ constexpr int kBatch = 128;
 constexpr int kStages = 4;
 constexpr int kConsumerWarps = 8;
 constexpr int kBlendThreads = (kConsumerWarps + 1) * 32;
+constexpr int kQueue = 16;        // queued survivors per warp before phase 2 runs
+constexpr int kQStride = 33;      // row stride of the queue in floats: conflict-free for both phases
 
 struct __align__(128) BwdSmem {
     float4 A[kStages][kBatch];
@@ -29,36 +37,63 @@ struct __align__(128) BwdSmem {
     uint64_t full[kStages];
     uint64_t empty[kStages];
     uint32_t nmax;
+    uint32_t pad[15];
+    float4 meta[kConsumerWarps][kQueue][2];       // {gx-x0, gy-y0, conic.x, conic.y}, {conic.z, opacity, bits(id), -}
+    float qw[kConsumerWarps][kQueue][kQStride];   // w  = G * dL/dG      per (slot, pixel)
+    float qc[kConsumerWarps][kQueue][kQStride];   // ca = alpha * T      per (slot, pixel)
+    float dL[kConsumerWarps][3][32];              // dL/dpixel of the warp's 32 pixels
 };
 
-// Reduces v[0..8] over the warp; on return lane `slot_lane(q)` holds the total of quantity q in the
-// returned value: lanes {0,2,4,8,10,16,18,20,24} <-> q {0..8}; every other lane returns garbage/zero.
-__device__ __forceinline__ float butterfly9(float v0, float v1, float v2, float v3, float v4, float v5,
-                                            float v6, float v7, float v8, int lane) {
+// 1/x for x in [0.01, 1]: MUFU.RCP + one Newton step (error < 1 ulp; the reference divides, IEEE).
+__device__ __forceinline__ float fast_rcp(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return fmaf(r, fmaf(-x, r, 1.0f), r);
+}
+
+// Phase 2: lanes (s, half) = (lane & 15, lane >> 4) sweep pixels [16*half, 16*half+16) of queue slot s.
+__device__ __forceinline__ void flush_queue(BwdSmem& sm, int warp, int lane, int count, float ddelx_dx,
+                                            float ddely_dy, float* __restrict__ accum) {
+    __syncwarp();
+    const int s = lane & 15, half = lane >> 4;
+    const float4 m0 = sm.meta[warp][s][0], m1 = sm.meta[warp][s][1];
+    const float gxr = m0.x, gyr = m0.y - (float)(2 * half);
+    const float* qw = &sm.qw[warp][s][16 * half];
+    const float* qc = &sm.qc[warp][s][16 * half];
+    const float* d0 = &sm.dL[warp][0][16 * half];
+    const float* d1 = &sm.dL[warp][1][16 * half];
+    const float* d2 = &sm.dL[warp][2][16 * half];
+    float Sw = 0.f, Swx = 0.f, Swy = 0.f, Sxx = 0.f, Sxy = 0.f, Syy = 0.f, C0 = 0.f, C1 = 0.f, C2 = 0.f;
+#pragma unroll
+    for (int it = 0; it < 16; ++it) {
+        const float w = qw[it], ca = qc[it];
+        const float dx = gxr - (float)(it & 7), dy = gyr - (float)(it >> 3);
+        const float wdx = w * dx, wdy = w * dy;
+        Sw += w; Swx += wdx; Swy += wdy;
+        Sxx = fmaf(wdx, dx, Sxx); Sxy = fmaf(wdx, dy, Sxy); Syy = fmaf(wdy, dy, Syy);
+        C0 = fmaf(ca, d0[it], C0); C1 = fmaf(ca, d1[it], C1); C2 = fmaf(ca, d2[it], C2);
+    }
     constexpr uint32_t full = 0xffffffffu;
-    const bool u16 = lane & 16, u8 = lane & 8, u4 = lane & 4, u2 = lane & 2;
-    // xor 16: 9 -> 5
-    float k0 = u16 ? v5 : v0, k1 = u16 ? v6 : v1, k2 = u16 ? v7 : v2, k3 = u16 ? v8 : v3, k4 = u16 ? 0.f : v4;
-    k0 += __shfl_xor_sync(full, u16 ? v0 : v5, 16);
-    k1 += __shfl_xor_sync(full, u16 ? v1 : v6, 16);
-    k2 += __shfl_xor_sync(full, u16 ? v2 : v7, 16);
-    k3 += __shfl_xor_sync(full, u16 ? v3 : v8, 16);
-    k4 += __shfl_xor_sync(full, u16 ? v4 : 0.f, 16);
-    // xor 8: 5 -> 3
-    float m0 = u8 ? k3 : k0, m1 = u8 ? k4 : k1, m2 = u8 ? 0.f : k2;
-    m0 += __shfl_xor_sync(full, u8 ? k0 : k3, 8);
-    m1 += __shfl_xor_sync(full, u8 ? k1 : k4, 8);
-    m2 += __shfl_xor_sync(full, u8 ? k2 : 0.f, 8);
-    // xor 4: 3 -> 2
-    float n0 = u4 ? m2 : m0, n1 = u4 ? 0.f : m1;
-    n0 += __shfl_xor_sync(full, u4 ? m0 : m2, 4);
-    n1 += __shfl_xor_sync(full, u4 ? m1 : 0.f, 4);
-    // xor 2: 2 -> 1
-    float o = u2 ? n1 : n0;
-    o += __shfl_xor_sync(full, u2 ? n0 : n1, 2);
-    // xor 1
-    o += __shfl_xor_sync(full, o, 1);
-    return o;
+    Sw += __shfl_xor_sync(full, Sw, 16);   Swx += __shfl_xor_sync(full, Swx, 16);
+    Swy += __shfl_xor_sync(full, Swy, 16); Sxx += __shfl_xor_sync(full, Sxx, 16);
+    Sxy += __shfl_xor_sync(full, Sxy, 16); Syy += __shfl_xor_sync(full, Syy, 16);
+    C0 += __shfl_xor_sync(full, C0, 16);   C1 += __shfl_xor_sync(full, C1, 16);
+    C2 += __shfl_xor_sync(full, C2, 16);
+    if (lane < count) {
+        // dG/ddelx = -G (dx a + dy b), dG/ddely = -G (dy c + dx b)   (backward.cu:539-546)
+        const float a = m0.z, b = m0.w, c = m1.x, op = m1.y;
+        float* row = accum + (size_t)__float_as_uint(m1.z) * kAccumStride;
+        atomicAdd(row + 0, -(a * Swx + b * Swy) * ddelx_dx);
+        atomicAdd(row + 1, -(c * Swy + b * Swx) * ddely_dy);
+        atomicAdd(row + 2, -0.5f * Sxx);
+        atomicAdd(row + 3, -0.5f * Sxy);
+        atomicAdd(row + 4, -0.5f * Syy);
+        atomicAdd(row + 5, Sw / op);           // G dL/dalpha = w / opacity  (dL/dG = opacity dL/dalpha)
+        atomicAdd(row + 6, C0);
+        atomicAdd(row + 7, C1);
+        atomicAdd(row + 8, C2);
+    }
+    __syncwarp();
 }
 
 __global__ void __launch_bounds__(kBlendThreads)
@@ -67,7 +102,8 @@ blend_backward_kernel(const uint2* __restrict__ ranges, const float4* __restrict
                       int W, int H, uint32_t grid_x, const float* __restrict__ bg,
                       const float* __restrict__ final_T, const uint32_t* __restrict__ n_contrib,
                       const float* __restrict__ dL_dpix, float* __restrict__ accum) {
-    __shared__ BwdSmem sm;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    BwdSmem& sm = *reinterpret_cast<BwdSmem*>(smem_raw);
     const uint32_t tile = blockIdx.x;
     const uint2 range = ranges[tile];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -79,7 +115,6 @@ blend_backward_kernel(const uint2* __restrict__ ranges, const float4* __restrict
     }
     __syncthreads();
 
-    // pixel state (consumer warps)
     const uint32_t tx = tile % grid_x, ty = tile / grid_x;
     const int x0 = (int)tx * kTile + (warp & 1) * 8, y0 = (int)ty * kTile + (warp >> 1) * 4;
     const int px = x0 + (lane & 7), py = y0 + (lane >> 3);
@@ -89,6 +124,9 @@ blend_backward_kernel(const uint2* __restrict__ ranges, const float4* __restrict
     const uint32_t nc = inside ? n_contrib[pix] : 0u;
     const uint32_t warp_nc = __reduce_max_sync(0xffffffffu, nc);
     if (lane == 0 && warp_nc > 0u) atomicMax(&sm.nmax, warp_nc);
+    float dL0 = 0.f, dL1 = 0.f, dL2 = 0.f;
+    if (inside) { dL0 = dL_dpix[pix]; dL1 = dL_dpix[hw + pix]; dL2 = dL_dpix[2 * hw + pix]; }
+    if (warp < kConsumerWarps) { sm.dL[warp][0][lane] = dL0; sm.dL[warp][1][lane] = dL1; sm.dL[warp][2][lane] = dL2; }
     __syncthreads();
     const int m = (int)sm.nmax;                 // entries [0, m) of the tile list can matter
     const int nb = (m + kBatch - 1) / kBatch;
@@ -112,18 +150,12 @@ blend_backward_kernel(const uint2* __restrict__ ranges, const float4* __restrict
 
     const float pxf = (float)px, pyf = (float)py;
     const float fx0 = (float)x0, fx1 = (float)(x0 + 7), fy0 = (float)y0, fy1 = (float)(y0 + 3);
-    float dL0 = 0.f, dL1 = 0.f, dL2 = 0.f;
-    if (inside) { dL0 = dL_dpix[pix]; dL1 = dL_dpix[hw + pix]; dL2 = dL_dpix[2 * hw + pix]; }
     const float bg_dot = __ldg(bg) * dL0 + __ldg(bg + 1) * dL1 + __ldg(bg + 2) * dL2;
     const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;  // pixel -> NDC (backward.cu:452-453)
     float T = T_final;
     float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;          // accum_rec
     float last_alpha = 0.f, lc0 = 0.f, lc1 = 0.f, lc2 = 0.f;
-    // which accumulator slot this lane flushes after the butterfly
-    int slot = -1;
-    switch (lane) { case 0: slot = 0; break; case 2: slot = 1; break; case 4: slot = 2; break;
-                    case 8: slot = 3; break; case 10: slot = 4; break; case 16: slot = 5; break;
-                    case 18: slot = 6; break; case 20: slot = 7; break; case 24: slot = 8; break; default: break; }
+    int qn = 0;                                        // queued survivors (warp-uniform)
 
     for (int k = 0; k < nb; ++k) {
         const int s = k % kStages;
@@ -152,41 +184,36 @@ blend_backward_kernel(const uint2* __restrict__ ranges, const float4* __restrict
                     const bool active = ((uint32_t)(lo + j) < nc) && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
                     if (!__any_sync(0xffffffffu, active)) continue;
                     const float4 col = sm.C[s][j];
-                    float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f, v4 = 0.f, v5 = 0.f, v6 = 0.f, v7 = 0.f, v8 = 0.f;
+                    float w = 0.f, ca = 0.f;
                     if (active) {
-                        T = T / (1.f - alpha);
-                        const float dchannel_dcolor = alpha * T;
-                        acc0 = last_alpha * lc0 + (1.f - last_alpha) * acc0;
-                        acc1 = last_alpha * lc1 + (1.f - last_alpha) * acc1;
-                        acc2 = last_alpha * lc2 + (1.f - last_alpha) * acc2;
+                        const float ir = fast_rcp(1.f - alpha);
+                        T = T * ir;
+                        ca = alpha * T;
+                        const float om = 1.f - last_alpha;
+                        acc0 = fmaf(last_alpha, lc0, om * acc0);
+                        acc1 = fmaf(last_alpha, lc1, om * acc1);
+                        acc2 = fmaf(last_alpha, lc2, om * acc2);
                         lc0 = col.x; lc1 = col.y; lc2 = col.z;
                         float dL_dalpha = (col.x - acc0) * dL0 + (col.y - acc1) * dL1 + (col.z - acc2) * dL2;
-                        dL_dalpha *= T;
+                        dL_dalpha = fmaf(dL_dalpha, T, -(T_final * ir) * bg_dot);
                         last_alpha = alpha;
-                        dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot;
-                        const float dL_dG = q.w * dL_dalpha;
-                        const float gdx = G * dx, gdy = G * dy;
-                        const float dG_ddelx = -gdx * q.x - gdy * q.y;
-                        const float dG_ddely = -gdy * q.z - gdx * q.y;
-                        v0 = dL_dG * dG_ddelx * ddelx_dx;
-                        v1 = dL_dG * dG_ddely * ddely_dy;
-                        v2 = -0.5f * gdx * dx * dL_dG;
-                        v3 = -0.5f * gdx * dy * dL_dG;
-                        v4 = -0.5f * gdy * dy * dL_dG;
-                        v5 = G * dL_dalpha;
-                        v6 = dchannel_dcolor * dL0;
-                        v7 = dchannel_dcolor * dL1;
-                        v8 = dchannel_dcolor * dL2;
+                        w = G * (q.w * dL_dalpha);
                     }
-                    const float total = butterfly9(v0, v1, v2, v3, v4, v5, v6, v7, v8, lane);
-                    if (slot >= 0)
-                        atomicAdd(accum + (size_t)__float_as_uint(col.w) * kAccumStride + slot, total);
+                    sm.qw[warp][qn][lane] = w;
+                    sm.qc[warp][qn][lane] = ca;
+                    if (lane == 0) {
+                        sm.meta[warp][qn][0] = make_float4(a.x - fx0, a.y - fy0, q.x, q.y);
+                        sm.meta[warp][qn][1] = make_float4(q.z, q.w, col.w, 0.f);
+                    }
+                    if (++qn == kQueue) { flush_queue(sm, warp, lane, kQueue, ddelx_dx, ddely_dy, accum); qn = 0; }
                 }
             }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&sm.empty[s]);
     }
+    // rows >= qn hold stale data; flush_queue only writes rows < qn
+    if (qn > 0) flush_queue(sm, warp, lane, qn, ddelx_dx, ddely_dy, accum);
 }
 
 }  // namespace
@@ -196,10 +223,12 @@ int launch_blend_backward(const sb_settings& s, int R, const BinningWs& b, const
     if (R <= 0) return SB_OK;
     const int W = s.image_width, H = s.image_height;
     const uint32_t gx = (W + kTile - 1) / kTile, gy = (H + kTile - 1) / kTile;
+    SB_CUDA_CHECK(cudaFuncSetAttribute(blend_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)sizeof(BwdSmem)));
     ScopedStage _p(kStBlendBwd, st);
-    blend_backward_kernel<<<gx * gy, kBlendThreads, 0, st>>>(img.ranges, b.recA, b.recB, b.recC, W, H, gx,
-                                                             s.bg, img.final_T, img.n_contrib,
-                                                             dL_dout_color, accum);
+    blend_backward_kernel<<<gx * gy, kBlendThreads, sizeof(BwdSmem), st>>>(img.ranges, b.recA, b.recB, b.recC, W, H,
+                                                                           gx, s.bg, img.final_T, img.n_contrib,
+                                                                           dL_dout_color, accum);
     SB_LAUNCH_CHECK("blend_backward_kernel");
     return SB_OK;
 }
