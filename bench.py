@@ -162,14 +162,28 @@ def e2e_step_fn(scene, dev, Rast, Settings):
     h2d = sum(t.numel() * 4 for t in host.values()) + host_dL.numel() * 4
     d2h = (out_color.numel() + out_depth.numel()) * 4
 
+    copy_stream = torch.cuda.Stream(dev)
+
     def step():
+        # The raster inputs go up on the compute stream; dL/dcolor (needed only by the backward) goes up on a
+        # side stream and the images come down on it while the backward runs.  Same orchestration for both arms.
+        cur = torch.cuda.current_stream(dev)
+        with torch.cuda.stream(copy_stream):
+            dL = host_dL.to(dev, non_blocking=True)
+            dl_ready = torch.cuda.Event(); dl_ready.record(copy_stream)
         inp = {k: v.to(dev, non_blocking=True).requires_grad_(True) for k, v in host.items()}
         inp["means2D"] = torch.zeros_like(inp["means3D"], requires_grad=True)
-        dL = host_dL.to(dev, non_blocking=True)
         color, radii, depth = rast(**inp)
+        fwd_done = torch.cuda.Event(); fwd_done.record(cur)
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(fwd_done)
+            out_color.copy_(color.detach(), non_blocking=True)
+            out_depth.copy_(depth.detach(), non_blocking=True)
+            d2h_done = torch.cuda.Event(); d2h_done.record(copy_stream)
+        cur.wait_event(dl_ready)
+        dL.record_stream(cur)
         color.backward(dL)
-        out_color.copy_(color.detach(), non_blocking=True)
-        out_depth.copy_(depth.detach(), non_blocking=True)
+        cur.wait_event(d2h_done)        # the step ends when both the gradients and the host images are complete
     return step, h2d, d2h
 
 

@@ -18,6 +18,7 @@
 // the arithmetic runs in phase 2 with all 32 lanes busy.
 #include "common.cuh"
 #include "pipeline.cuh"
+#include <stdlib.h>
 
 namespace sb {
 
@@ -27,9 +28,10 @@ constexpr int kBatch = 128;
 constexpr int kStages = 4;
 constexpr int kConsumerWarps = 8;
 constexpr int kBlendThreads = (kConsumerWarps + 1) * 32;
-constexpr int kQueue = 16;        // queued survivors per warp before phase 2 runs
 constexpr int kQStride = 33;      // row stride of the queue in floats: conflict-free for both phases
 
+// kQueue = queued survivors per warp before phase 2 runs (16: two lanes per Gaussian, 8: four lanes)
+template <int kQueue>
 struct __align__(128) BwdSmem {
     float4 A[kStages][kBatch];
     float4 B[kStages][kBatch];
@@ -51,21 +53,30 @@ __device__ __forceinline__ float fast_rcp(float x) {
     return fmaf(r, fmaf(-x, r, 1.0f), r);
 }
 
-// Phase 2: lanes (s, half) = (lane & 15, lane >> 4) sweep pixels [16*half, 16*half+16) of queue slot s.
-__device__ __forceinline__ void flush_queue(BwdSmem& sm, int warp, int lane, int count, float ddelx_dx,
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void sts_v4(uint32_t addr, float a, float b, float c, float d) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// Phase 2: lanes (s, part) = (lane % kQueue, lane / kQueue) sweep pixels [kQueue*part, kQueue*(part+1))
+// of queue slot s (kQueue pixels per lane, 32/kQueue lanes per queued Gaussian).
+template <int kQueue>
+__device__ __forceinline__ void flush_queue(BwdSmem<kQueue>& sm, int warp, int lane, int count, float ddelx_dx,
                                             float ddely_dy, float* __restrict__ accum) {
     __syncwarp();
-    const int s = lane & 15, half = lane >> 4;
+    const int s = lane % kQueue, part = lane / kQueue;
     const float4 m0 = sm.meta[warp][s][0], m1 = sm.meta[warp][s][1];
-    const float gxr = m0.x, gyr = m0.y - (float)(2 * half);
-    const float* qw = &sm.qw[warp][s][16 * half];
-    const float* qc = &sm.qc[warp][s][16 * half];
-    const float* d0 = &sm.dL[warp][0][16 * half];
-    const float* d1 = &sm.dL[warp][1][16 * half];
-    const float* d2 = &sm.dL[warp][2][16 * half];
+    const float gxr = m0.x, gyr = m0.y - (float)((kQueue / 8) * part);
+    const float* qw = &sm.qw[warp][s][kQueue * part];
+    const float* qc = &sm.qc[warp][s][kQueue * part];
+    const float* d0 = &sm.dL[warp][0][kQueue * part];
+    const float* d1 = &sm.dL[warp][1][kQueue * part];
+    const float* d2 = &sm.dL[warp][2][kQueue * part];
     float Sw = 0.f, Swx = 0.f, Swy = 0.f, Sxx = 0.f, Sxy = 0.f, Syy = 0.f, C0 = 0.f, C1 = 0.f, C2 = 0.f;
 #pragma unroll
-    for (int it = 0; it < 16; ++it) {
+    for (int it = 0; it < kQueue; ++it) {
         const float w = qw[it], ca = qc[it];
         const float dx = gxr - (float)(it & 7), dy = gyr - (float)(it >> 3);
         const float wdx = w * dx, wdy = w * dy;
@@ -74,11 +85,14 @@ __device__ __forceinline__ void flush_queue(BwdSmem& sm, int warp, int lane, int
         C0 = fmaf(ca, d0[it], C0); C1 = fmaf(ca, d1[it], C1); C2 = fmaf(ca, d2[it], C2);
     }
     constexpr uint32_t full = 0xffffffffu;
-    Sw += __shfl_xor_sync(full, Sw, 16);   Swx += __shfl_xor_sync(full, Swx, 16);
-    Swy += __shfl_xor_sync(full, Swy, 16); Sxx += __shfl_xor_sync(full, Sxx, 16);
-    Sxy += __shfl_xor_sync(full, Sxy, 16); Syy += __shfl_xor_sync(full, Syy, 16);
-    C0 += __shfl_xor_sync(full, C0, 16);   C1 += __shfl_xor_sync(full, C1, 16);
-    C2 += __shfl_xor_sync(full, C2, 16);
+#pragma unroll
+    for (int off = kQueue; off < 32; off <<= 1) {
+        Sw += __shfl_xor_sync(full, Sw, off);   Swx += __shfl_xor_sync(full, Swx, off);
+        Swy += __shfl_xor_sync(full, Swy, off); Sxx += __shfl_xor_sync(full, Sxx, off);
+        Sxy += __shfl_xor_sync(full, Sxy, off); Syy += __shfl_xor_sync(full, Syy, off);
+        C0 += __shfl_xor_sync(full, C0, off);   C1 += __shfl_xor_sync(full, C1, off);
+        C2 += __shfl_xor_sync(full, C2, off);
+    }
     if (lane < count) {
         // dG/ddelx = -G (dx a + dy b), dG/ddely = -G (dy c + dx b)   (backward.cu:539-546)
         const float a = m0.z, b = m0.w, c = m1.x, op = m1.y;
@@ -96,14 +110,15 @@ __device__ __forceinline__ void flush_queue(BwdSmem& sm, int warp, int lane, int
     __syncwarp();
 }
 
-__global__ void __launch_bounds__(kBlendThreads)
+template <int kQueue, int kMinBlocks>
+__global__ void __launch_bounds__(kBlendThreads, kMinBlocks)
 blend_backward_kernel(const uint2* __restrict__ ranges, const float4* __restrict__ recA,
                       const float4* __restrict__ recB, const float4* __restrict__ recC,
                       int W, int H, uint32_t grid_x, const float* __restrict__ bg,
                       const float* __restrict__ final_T, const uint32_t* __restrict__ n_contrib,
                       const float* __restrict__ dL_dpix, float* __restrict__ accum) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    BwdSmem& sm = *reinterpret_cast<BwdSmem*>(smem_raw);
+    BwdSmem<kQueue>& sm = *reinterpret_cast<BwdSmem<kQueue>*>(smem_raw);
     const uint32_t tile = blockIdx.x;
     const uint2 range = ranges[tile];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -156,6 +171,12 @@ blend_backward_kernel(const uint2* __restrict__ ranges, const float4* __restrict
     float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;          // accum_rec
     float last_alpha = 0.f, lc0 = 0.f, lc1 = 0.f, lc2 = 0.f;
     int qn = 0;                                        // queued survivors (warp-uniform)
+    // shared-space addresses of this lane's queue column and of the warp's meta rows (explicit st.shared:
+    // keeps the generic->shared window arithmetic out of the inner loop)
+    const uint32_t qw_lane = smem_u32(&sm.qw[warp][0][lane]);
+    const uint32_t qc_lane = smem_u32(&sm.qc[warp][0][lane]);
+    const uint32_t meta_row = smem_u32(&sm.meta[warp][0][0]);
+    uint32_t qoff = 0;                                 // qn * kQStride * 4
 
     for (int k = 0; k < nb; ++k) {
         const int s = k % kStages;
@@ -199,13 +220,17 @@ blend_backward_kernel(const uint2* __restrict__ ranges, const float4* __restrict
                         last_alpha = alpha;
                         w = G * (q.w * dL_dalpha);
                     }
-                    sm.qw[warp][qn][lane] = w;
-                    sm.qc[warp][qn][lane] = ca;
+                    sts_f32(qw_lane + qoff, w);
+                    sts_f32(qc_lane + qoff, ca);
                     if (lane == 0) {
-                        sm.meta[warp][qn][0] = make_float4(a.x - fx0, a.y - fy0, q.x, q.y);
-                        sm.meta[warp][qn][1] = make_float4(q.z, q.w, col.w, 0.f);
+                        sts_v4(meta_row + qn * 32, a.x - fx0, a.y - fy0, q.x, q.y);
+                        sts_v4(meta_row + qn * 32 + 16, q.z, q.w, col.w, 0.f);
                     }
-                    if (++qn == kQueue) { flush_queue(sm, warp, lane, kQueue, ddelx_dx, ddely_dy, accum); qn = 0; }
+                    qoff += kQStride * 4;
+                    if (++qn == kQueue) {
+                        flush_queue<kQueue>(sm, warp, lane, kQueue, ddelx_dx, ddely_dy, accum);
+                        qn = 0; qoff = 0;
+                    }
                 }
             }
         }
@@ -213,7 +238,7 @@ blend_backward_kernel(const uint2* __restrict__ ranges, const float4* __restrict
         if (lane == 0) mbar_arrive(&sm.empty[s]);
     }
     // rows >= qn hold stale data; flush_queue only writes rows < qn
-    if (qn > 0) flush_queue(sm, warp, lane, qn, ddelx_dx, ddely_dy, accum);
+    if (qn > 0) flush_queue<kQueue>(sm, warp, lane, qn, ddelx_dx, ddely_dy, accum);
 }
 
 }  // namespace
@@ -223,12 +248,22 @@ int launch_blend_backward(const sb_settings& s, int R, const BinningWs& b, const
     if (R <= 0) return SB_OK;
     const int W = s.image_width, H = s.image_height;
     const uint32_t gx = (W + kTile - 1) / kTile, gy = (H + kTile - 1) / kTile;
-    SB_CUDA_CHECK(cudaFuncSetAttribute(blend_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)sizeof(BwdSmem)));
-    ScopedStage _p(kStBlendBwd, st);
-    blend_backward_kernel<<<gx * gy, kBlendThreads, sizeof(BwdSmem), st>>>(img.ranges, b.recA, b.recB, b.recC, W, H,
-                                                                           gx, s.bg, img.final_T, img.n_contrib,
-                                                                           dL_dout_color, accum);
+    static const int variant = [] { const char* e = getenv("SB_BWD_VARIANT"); return e ? atoi(e) : 0; }();
+#define SB_LAUNCH_BWD(Q, MB)                                                                                   \
+    do {                                                                                                       \
+        SB_CUDA_CHECK(cudaFuncSetAttribute(blend_backward_kernel<Q, MB>,                                       \
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BwdSmem<Q>))); \
+        ScopedStage _p(kStBlendBwd, st);                                                                       \
+        blend_backward_kernel<Q, MB><<<gx * gy, kBlendThreads, sizeof(BwdSmem<Q>), st>>>(                      \
+            img.ranges, b.recA, b.recB, b.recC, W, H, gx, s.bg, img.final_T, img.n_contrib, dL_dout_color, accum); \
+    } while (0)
+    switch (variant) {
+        case 1: SB_LAUNCH_BWD(8, 4); break;
+        case 2: SB_LAUNCH_BWD(16, 2); break;
+        case 3: SB_LAUNCH_BWD(8, 3); break;
+        default: SB_LAUNCH_BWD(16, 3); break;
+    }
+#undef SB_LAUNCH_BWD
     SB_LAUNCH_CHECK("blend_backward_kernel");
     return SB_OK;
 }

@@ -15,6 +15,7 @@
 //   3. a warp whose 32 pixels are all saturated (T < 1e-4) stops evaluating (warp-vote early-out).
 #include "common.cuh"
 #include "pipeline.cuh"
+#include <stdlib.h>
 
 namespace sb {
 
@@ -33,7 +34,8 @@ struct __align__(128) FwdSmem {
     uint64_t empty[kStages];
 };
 
-__global__ void __launch_bounds__(kBlendThreads)
+template <int kMinBlocks>
+__global__ void __launch_bounds__(kBlendThreads, kMinBlocks)
 blend_forward_kernel(const uint2* __restrict__ ranges, const float4* __restrict__ recA,
                      const float4* __restrict__ recB, const float4* __restrict__ recC,
                      const uint32_t* __restrict__ depth_key, int W, int H, uint32_t grid_x,
@@ -152,10 +154,16 @@ int launch_blend_forward(const sb_settings& s, int R, const GeometryWs& g, const
     (void)R;
     const int W = s.image_width, H = s.image_height;
     const uint32_t gx = (W + kTile - 1) / kTile, gy = (H + kTile - 1) / kTile;
+    static const int variant = [] { const char* e = getenv("SB_FWD_VARIANT"); return e ? atoi(e) : 0; }();
     ScopedStage _p(kStBlendFwd, st);
-    blend_forward_kernel<<<gx * gy, kBlendThreads, 0, st>>>(img.ranges, b.recA, b.recB, b.recC, g.depth_key,
-                                                            W, H, gx, s.bg, out_color, out_depth,
-                                                            img.final_T, img.n_contrib);
+    if (variant == 1)
+        blend_forward_kernel<7><<<gx * gy, kBlendThreads, 0, st>>>(img.ranges, b.recA, b.recB, b.recC, g.depth_key,
+                                                                   W, H, gx, s.bg, out_color, out_depth,
+                                                                   img.final_T, img.n_contrib);
+    else
+        blend_forward_kernel<5><<<gx * gy, kBlendThreads, 0, st>>>(img.ranges, b.recA, b.recB, b.recC, g.depth_key,
+                                                                   W, H, gx, s.bg, out_color, out_depth,
+                                                                   img.final_T, img.n_contrib);
     SB_LAUNCH_CHECK("blend_forward_kernel");
     return SB_OK;
 }

@@ -167,3 +167,33 @@ def test_api_edge_cases(cuda_device):
     vis = rast.markVisible(inp2["means3D"])
     assert vis.dtype == torch.bool and not vis.any()
     assert rast.markVisible(sc.inputs(dev)["means3D"]).all()
+
+
+def test_cov3d_precomp_branch_vs_reference(cuda_device):
+    """The cov3D_precomp branch of the operator API (X/cuda_rasterizer/forward.cu:203-214,
+    backward.cu:393-395): same images as the scale/rotation path, dL/dcov3D against the reference."""
+    ref = reference_extension()
+    import splatam_b200 as S
+    dev = cuda_device
+    sc = scenes.config1(seed=13, P=2000, w=160, h=96)
+    cov = torch.from_numpy(sc.oracle().geometry()["cov3D"]).to(dev)   # bit-exact Sigma of the scale/rot path
+    dL = torch.randn(3, sc.h, sc.w, generator=torch.Generator().manual_seed(5)).to(dev)
+
+    def run(mod):
+        rs = sc.settings(mod.GaussianRasterizationSettings, dev)
+        inp = sc.inputs(dev, requires_grad=True)
+        c = cov.clone().requires_grad_(True)
+        color, radii, depth = mod.GaussianRasterizer(rs)(means3D=inp["means3D"], means2D=inp["means2D"],
+                                                         opacities=inp["opacities"], colors_precomp=inp["colors_precomp"],
+                                                         cov3D_precomp=c)
+        color.backward(dL)
+        return color.detach().cpu().numpy(), radii.cpu().numpy(), c.grad.cpu().numpy(), inp["means3D"].grad.cpu().numpy()
+
+    col, rad, gcov, gmean = run(S)
+    # identical to the scale/rotation path
+    c0, r0, _ = S.GaussianRasterizer(sc.settings(S.GaussianRasterizationSettings, dev))(**sc.inputs(dev))
+    assert np.array_equal(col.view(np.uint32), c0.cpu().numpy().view(np.uint32)) and np.array_equal(rad, r0.cpu().numpy())
+    if ref is not None:
+        rcol, rrad, rgcov, rgmean = run(ref)
+        assert np.array_equal(col.view(np.uint32), rcol.view(np.uint32)) and np.array_equal(rad, rrad)
+        assert l2_rel(gcov, rgcov) < REL and l2_rel(gmean, rgmean) < REL
