@@ -151,6 +151,23 @@ SB_API int sb_export_binning(const sb_settings* s, int P, int num_rendered,
                       uint64_t* keys, uint32_t* point_list, uint32_t* ranges,
                       float* final_T, uint32_t* n_contrib, void* stream);
 
+/* ---- per-iteration training ops around the rasterizer -----------------
+ * sb_adam_step: torch.optim.Adam (no amsgrad / weight decay) over ONE flat parameter buffer whose segments
+ * [seg_end[k-1], seg_end[k]) have learning rates seg_lr[k] (host arrays, <= 16 segments); replaces the
+ * multi-group optimizer.step() of R/scripts/splatam.py:160-166,869.  `step` counts from 1.
+ * sb_image_loss_*: w_l1*mean|x-y| + w_ssim*(1-mean SSIM(x,y)) over [C,H,W] images with the reference's
+ * 11x11 sigma-1.5 Gaussian window and zero padding (R/utils/slam_external.py:54-97, R/scripts/splatam.py:290).
+ * forward writes sums[0] = sum of the SSIM map, sums[1] = sum|x-y| (device doubles) and 3*C*H*W floats of
+ * partial derivatives into `work`; backward turns them into d loss / d x given the upstream scalar grad. */
+SB_API int sb_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, size_t n,
+                        const uint32_t* seg_end, const float* seg_lr, int num_segments, int step,
+                        float beta1, float beta2, float eps, void* stream);
+SB_API size_t sb_image_loss_workspace_floats(int C, int H, int W);
+SB_API int sb_image_loss_forward(const float* x, const float* y, int C, int H, int W, float* work,
+                                 double* sums, void* stream);
+SB_API int sb_image_loss_backward(const float* x, const float* y, int C, int H, int W, const float* work,
+                                  const float* grad_out, float w_ssim, float w_l1, float* grad_x, void* stream);
+
 /* ---- per-stage device timing (measurement only; bench.py's roofline pass) -------------------
  * Between sb_profile_begin() and sb_profile_end() every stage launch of this process is bracketed
  * by CUDA events on its stream.  sb_profile_end synchronises, writes the summed milliseconds and call

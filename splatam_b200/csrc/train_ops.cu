@@ -1,0 +1,234 @@
+// train_ops.cu -- the two per-iteration PyTorch costs that dominate SplaTAM's mapping step once the
+// rasterizer is fast, as hand-written kernels:
+//   * fused Adam over the packed (flat) Gaussian parameter buffer with per-segment learning rates
+//     (reference: torch.optim.Adam over 5-7 param groups, R/scripts/splatam.py:160-166,869);
+//   * fused image loss  0.8*L1 + 0.2*(1-SSIM)  and its gradient w.r.t. the rendered image
+//     (reference: l1_loss_v1 + calc_ssim, R/scripts/splatam.py:290, R/utils/slam_external.py:54-97 --
+//     five depthwise 11x11 convolutions forward and their autograd backward).
+#include "common.cuh"
+
+namespace sb {
+
+namespace {
+
+constexpr int kMaxSeg = 16;
+struct AdamSegs { uint32_t end[kMaxSeg]; float lr[kMaxSeg]; int n; };
+
+__global__ void __launch_bounds__(256)
+adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+            size_t n, AdamSegs segs, float beta1, float beta2, float eps, float bc1, float bc2_sqrt) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float lr = 0.f;
+#pragma unroll 4
+    for (int k = 0; k < segs.n; ++k)
+        if (i < segs.end[k]) { lr = segs.lr[k]; break; }
+    const float gi = g[i];
+    // torch.optim.Adam single-tensor math: lerp, addcmul, sqrt / bias-correction + eps, addcdiv
+    const float mi = fmaf(gi - m[i], 1.0f - beta1, m[i]);
+    const float vi = fmaf(gi * gi, 1.0f - beta2, v[i] * beta2);
+    m[i] = mi; v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] = p[i] - (lr / bc1) * (mi / denom);
+}
+
+// ---- fused 0.8*L1 + 0.2*(1-SSIM) ----------------------------------------------------------------------
+constexpr int kTW = 32, kTH = 8, kR = 5, kWin = 11;     // output tile 32x8, 11-tap separable Gaussian
+constexpr int kPW = kTW + 2 * kR, kPH = kTH + 2 * kR;   // padded tile 42 x 18
+__constant__ float c_gauss[kWin];
+
+// Forward: per pixel/channel SSIM map terms; writes the three partial-derivative maps needed by the
+// backward (dS/dmu1, dS/dE[x^2], dS/dE[xy]) and accumulates sum(ssim) and sum|x-y| into sums[0..1].
+__global__ void __launch_bounds__(kTW * kTH)
+ssim_l1_forward_kernel(const float* __restrict__ x, const float* __restrict__ y, int C, int H, int W,
+                       float* __restrict__ dmu, float* __restrict__ de11, float* __restrict__ de12,
+                       double* __restrict__ sums) {
+    __shared__ float sx[kPH][kPW], sy[kPH][kPW];
+    __shared__ float h[5][kPH][kTW];     // horizontally filtered x, y, xx, yy, xy
+    __shared__ float red[2][kTW * kTH / 32];
+    const int c = blockIdx.z, x0 = blockIdx.x * kTW, y0 = blockIdx.y * kTH;
+    const float* xc = x + (size_t)c * H * W;
+    const float* yc = y + (size_t)c * H * W;
+    const int tid = threadIdx.y * kTW + threadIdx.x;
+    for (int i = tid; i < kPH * kPW; i += kTW * kTH) {
+        const int r = i / kPW, q = i % kPW, gy = y0 + r - kR, gx = x0 + q - kR;
+        const bool in = gy >= 0 && gy < H && gx >= 0 && gx < W;          // zero padding (conv2d padding=5)
+        sx[r][q] = in ? __ldg(xc + (size_t)gy * W + gx) : 0.f;
+        sy[r][q] = in ? __ldg(yc + (size_t)gy * W + gx) : 0.f;
+    }
+    __syncthreads();
+    for (int i = tid; i < kPH * kTW; i += kTW * kTH) {
+        const int r = i / kTW, q = i % kTW;
+        float a = 0.f, b = 0.f, aa = 0.f, bb = 0.f, ab = 0.f;
+#pragma unroll
+        for (int k = 0; k < kWin; ++k) {
+            const float w = c_gauss[k], xv = sx[r][q + k], yv = sy[r][q + k];
+            a = fmaf(w, xv, a); b = fmaf(w, yv, b);
+            aa = fmaf(w, xv * xv, aa); bb = fmaf(w, yv * yv, bb); ab = fmaf(w, xv * yv, ab);
+        }
+        h[0][r][q] = a; h[1][r][q] = b; h[2][r][q] = aa; h[3][r][q] = bb; h[4][r][q] = ab;
+    }
+    __syncthreads();
+    const int px = x0 + threadIdx.x, py = y0 + threadIdx.y;
+    float ssim = 0.f, l1 = 0.f;
+    if (px < W && py < H) {
+        float mu1 = 0.f, mu2 = 0.f, e11 = 0.f, e22 = 0.f, e12 = 0.f;
+#pragma unroll
+        for (int k = 0; k < kWin; ++k) {
+            const float w = c_gauss[k];
+            mu1 = fmaf(w, h[0][threadIdx.y + k][threadIdx.x], mu1);
+            mu2 = fmaf(w, h[1][threadIdx.y + k][threadIdx.x], mu2);
+            e11 = fmaf(w, h[2][threadIdx.y + k][threadIdx.x], e11);
+            e22 = fmaf(w, h[3][threadIdx.y + k][threadIdx.x], e22);
+            e12 = fmaf(w, h[4][threadIdx.y + k][threadIdx.x], e12);
+        }
+        const float C1 = 0.01f * 0.01f, C2 = 0.03f * 0.03f;
+        const float s1 = e11 - mu1 * mu1, s2 = e22 - mu2 * mu2, s12 = e12 - mu1 * mu2;
+        const float a1 = 2.f * mu1 * mu2 + C1, a2 = 2.f * s12 + C2, b1 = mu1 * mu1 + mu2 * mu2 + C1, b2 = s1 + s2 + C2;
+        const float inv = 1.f / (b1 * b2);
+        ssim = a1 * a2 * inv;
+        const size_t o = (size_t)c * H * W + (size_t)py * W + px;
+        // total derivatives w.r.t. mu1 (incl. through sigma terms), E[x^2], E[xy]
+        dmu[o] = 2.f * mu2 * (a2 - a1) * inv - ssim * 2.f * mu1 * (1.f / b1 - 1.f / b2);
+        de11[o] = -ssim / b2;
+        de12[o] = 2.f * a1 * inv;
+        l1 = fabsf(sx[threadIdx.y + kR][threadIdx.x + kR] - sy[threadIdx.y + kR][threadIdx.x + kR]);
+    }
+    // block reduction of the two sums
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        ssim += __shfl_xor_sync(0xffffffffu, ssim, off);
+        l1 += __shfl_xor_sync(0xffffffffu, l1, off);
+    }
+    if ((tid & 31) == 0) { red[0][tid >> 5] = ssim; red[1][tid >> 5] = l1; }
+    __syncthreads();
+    if (tid == 0) {
+        float a = 0.f, b = 0.f;
+        for (int i = 0; i < kTW * kTH / 32; ++i) { a += red[0][i]; b += red[1][i]; }
+        atomicAdd(&sums[0], (double)a);
+        atomicAdd(&sums[1], (double)b);
+    }
+}
+
+// Backward: grad_x = gscale_ssim * (conv(dmu) + 2 x conv(de11) + y conv(de12)) + gscale_l1 * sign(x - y)
+__global__ void __launch_bounds__(kTW * kTH)
+ssim_l1_backward_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ dmu,
+                        const float* __restrict__ de11, const float* __restrict__ de12, int C, int H, int W,
+                        const float* __restrict__ grad_out, float w_ssim, float w_l1, float* __restrict__ gx) {
+    __shared__ float s[3][kPH][kPW];
+    __shared__ float h[3][kPH][kTW];
+    const int c = blockIdx.z, x0 = blockIdx.x * kTW, y0 = blockIdx.y * kTH;
+    const size_t plane = (size_t)c * H * W;
+    const int tid = threadIdx.y * kTW + threadIdx.x;
+    for (int i = tid; i < kPH * kPW; i += kTW * kTH) {
+        const int r = i / kPW, q = i % kPW, gy = y0 + r - kR, gxx = x0 + q - kR;
+        const bool in = gy >= 0 && gy < H && gxx >= 0 && gxx < W;
+        const size_t o = plane + (size_t)gy * W + gxx;
+        s[0][r][q] = in ? __ldg(dmu + o) : 0.f;
+        s[1][r][q] = in ? __ldg(de11 + o) : 0.f;
+        s[2][r][q] = in ? __ldg(de12 + o) : 0.f;
+    }
+    __syncthreads();
+    for (int i = tid; i < kPH * kTW; i += kTW * kTH) {
+        const int r = i / kTW, q = i % kTW;
+        float a = 0.f, b = 0.f, d = 0.f;
+#pragma unroll
+        for (int k = 0; k < kWin; ++k) {
+            const float w = c_gauss[k];
+            a = fmaf(w, s[0][r][q + k], a); b = fmaf(w, s[1][r][q + k], b); d = fmaf(w, s[2][r][q + k], d);
+        }
+        h[0][r][q] = a; h[1][r][q] = b; h[2][r][q] = d;
+    }
+    __syncthreads();
+    const int px = x0 + threadIdx.x, py = y0 + threadIdx.y;
+    if (px >= W || py >= H) return;
+    float a = 0.f, b = 0.f, d = 0.f;
+#pragma unroll
+    for (int k = 0; k < kWin; ++k) {
+        const float w = c_gauss[k];
+        a = fmaf(w, h[0][threadIdx.y + k][threadIdx.x], a);
+        b = fmaf(w, h[1][threadIdx.y + k][threadIdx.x], b);
+        d = fmaf(w, h[2][threadIdx.y + k][threadIdx.x], d);
+    }
+    const size_t o = plane + (size_t)py * W + px;
+    const float xv = x[o], yv = y[o], go = __ldg(grad_out);
+    const float n = (float)C * (float)H * (float)W;
+    // loss = w_l1 * mean|x-y| + w_ssim * (1 - mean(ssim))
+    const float diff = xv - yv;
+    const float sgn = diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f);
+    gx[o] = go * (w_l1 * sgn / n - w_ssim * (a + 2.f * xv * b + yv * d) / n);
+}
+
+bool g_gauss_ready = false;
+
+}  // namespace
+
+}  // namespace sb
+
+using namespace sb;
+
+extern "C" {
+
+SB_API int sb_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, size_t n,
+                        const uint32_t* seg_end, const float* seg_lr, int num_segments, int step, float beta1,
+                        float beta2, float eps, void* stream) {
+    if (!params || !grads || !exp_avg || !exp_avg_sq || !seg_end || !seg_lr || num_segments < 1 ||
+        num_segments > kMaxSeg || step < 1)
+        return SB_ERR_BAD_ARG;
+    if (n == 0) return SB_OK;
+    AdamSegs segs;
+    segs.n = num_segments;
+    for (int k = 0; k < num_segments; ++k) { segs.end[k] = seg_end[k]; segs.lr[k] = seg_lr[k]; }
+    const double bc1 = 1.0 - pow((double)beta1, step), bc2 = 1.0 - pow((double)beta2, step);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(params, grads, exp_avg, exp_avg_sq, n, segs, beta1, beta2,
+                                                              eps, (float)bc1, (float)sqrt(bc2));
+    SB_LAUNCH_CHECK("adam_kernel");
+    return SB_OK;
+}
+
+static int ensure_gauss() {
+    if (g_gauss_ready) return SB_OK;
+    float g[kWin]; double sum = 0.0;
+    for (int i = 0; i < kWin; ++i) { g[i] = (float)exp(-(double)((i - kWin / 2) * (i - kWin / 2)) / (2.0 * 1.5 * 1.5)); sum += g[i]; }
+    // slam_external.gaussian(): float32 exp values divided by their float32 sum
+    float fs = 0.f; for (int i = 0; i < kWin; ++i) fs += g[i];
+    for (int i = 0; i < kWin; ++i) g[i] = g[i] / fs;
+    (void)sum;
+    SB_CUDA_CHECK(cudaMemcpyToSymbol(c_gauss, g, sizeof(g)));
+    g_gauss_ready = true;
+    return SB_OK;
+}
+
+SB_API size_t sb_image_loss_workspace_floats(int C, int H, int W) { return (size_t)3 * C * H * W; }
+
+/* loss terms of  w_l1*mean|x-y| + w_ssim*(1-mean(SSIM(x,y))) : writes sums[0]=sum(ssim map), sums[1]=sum|x-y|
+ * (device doubles, zeroed here) and the partial-derivative maps into `work` (3*C*H*W floats). */
+SB_API int sb_image_loss_forward(const float* x, const float* y, int C, int H, int W, float* work, double* sums,
+                                 void* stream) {
+    if (!x || !y || !work || !sums || C < 1 || H < 1 || W < 1) return SB_ERR_BAD_ARG;
+    int rc = ensure_gauss();
+    if (rc != SB_OK) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    SB_CUDA_CHECK(cudaMemsetAsync(sums, 0, 2 * sizeof(double), st));
+    const size_t n = (size_t)C * H * W;
+    dim3 grid((W + kTW - 1) / kTW, (H + kTH - 1) / kTH, C), block(kTW, kTH);
+    ssim_l1_forward_kernel<<<grid, block, 0, st>>>(x, y, C, H, W, work, work + n, work + 2 * n, sums);
+    SB_LAUNCH_CHECK("ssim_l1_forward_kernel");
+    return SB_OK;
+}
+
+SB_API int sb_image_loss_backward(const float* x, const float* y, int C, int H, int W, const float* work,
+                                  const float* grad_out, float w_ssim, float w_l1, float* grad_x, void* stream) {
+    if (!x || !y || !work || !grad_out || !grad_x || C < 1 || H < 1 || W < 1) return SB_ERR_BAD_ARG;
+    int rc = ensure_gauss();
+    if (rc != SB_OK) return rc;
+    const size_t n = (size_t)C * H * W;
+    dim3 grid((W + kTW - 1) / kTW, (H + kTH - 1) / kTH, C), block(kTW, kTH);
+    ssim_l1_backward_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
+        x, y, work, work + n, work + 2 * n, C, H, W, grad_out, w_ssim, w_l1, grad_x);
+    SB_LAUNCH_CHECK("ssim_l1_backward_kernel");
+    return SB_OK;
+}
+
+}  // extern "C"

@@ -103,7 +103,7 @@ def calc_ssim(img1, img2, window_size=11):
     return (((2 * mu12 + c1) * (2 * s12 + c2)) / ((mu1_sq + mu2_sq + c1) * (s1 + s2 + c2))).mean()
 
 
-def mapping_loss(params, frame, render, loss_weights=(0.5, 1.0), ignore_outlier_depth_loss=False):
+def mapping_loss(params, frame, render, loss_weights=(0.5, 1.0), ignore_outlier_depth_loss=False, fused_loss=False):
     """SplaTAM get_loss(mapping=True): Gaussians get gradient, camera does not
     (R/scripts/splatam.py:214-347 with tracking=False, mapping=True, do_ba=False, use_l1=True).
     frame: dict(im [3,H,W], depth [1,H,W], cam settings, w2c [4,4] first-frame w2c, id time index).
@@ -119,7 +119,11 @@ def mapping_loss(params, frame, render, loss_weights=(0.5, 1.0), ignore_outlier_
         mask = mask & (err < 10 * err.median())
     mask = mask.detach()
     l_depth = torch.abs(frame["depth"] - depth)[mask].mean()
-    l_im = 0.8 * torch.abs(im - frame["im"]).mean() + 0.2 * (1.0 - calc_ssim(im, frame["im"]))
+    if fused_loss:      # one forward + one backward kernel instead of 5 depthwise convs + autograd (train_ops.cu)
+        from .train_ops import image_loss
+        l_im = image_loss(im, frame["im"], 0.8, 0.2)
+    else:
+        l_im = 0.8 * torch.abs(im - frame["im"]).mean() + 0.2 * (1.0 - calc_ssim(im, frame["im"]))
     return loss_weights[0] * l_im + loss_weights[1] * l_depth, radius
 
 
@@ -158,7 +162,8 @@ class ShardedMapper:
     DEFAULT_LRS = dict(means3D=0.0001, rgb_colors=0.0025, unnorm_rotations=0.001, logit_opacities=0.05,
                        log_scales=0.001)
 
-    def __init__(self, gaussians, cam_unnorm_rots, cam_trans, lrs=None, render=default_render, group=None, seed=0):
+    def __init__(self, gaussians, cam_unnorm_rots, cam_trans, lrs=None, render=default_render, group=None, seed=0,
+                 fused=None):
         import torch.distributed as dist
         self.dist = dist if (dist.is_available() and dist.is_initialized()) else None
         self.group = group
@@ -167,8 +172,16 @@ class ShardedMapper:
         self.g = FlatGaussians(gaussians)
         self.cam = dict(cam_unnorm_rots=cam_unnorm_rots.detach(), cam_trans=cam_trans.detach())
         lrs = dict(self.DEFAULT_LRS, **(lrs or {}))
-        self.opt = torch.optim.Adam([{"params": [self.g.params[k]], "name": k, "lr": lrs[k]} for k in GAUSSIAN_KEYS],
-                                    lr=0.0, eps=1e-15)
+        # fused = hand-written Adam over the flat buffer + fused L1/SSIM loss (CUDA only); the torch path is
+        # the reference formulation (R/scripts/splatam.py:160-166) and the one the CPU/gloo test exercises
+        self.fused = self.g.flat.is_cuda if fused is None else bool(fused)
+        if self.fused:
+            from .train_ops import FusedAdam
+            sizes = [math.prod(self.g.shapes[k]) for k in GAUSSIAN_KEYS]
+            self.opt = FusedAdam(self.g.flat, self.g.flat_grad, sizes, [lrs[k] for k in GAUSSIAN_KEYS], eps=1e-15)
+        else:
+            self.opt = torch.optim.Adam([{"params": [self.g.params[k]], "name": k, "lr": lrs[k]} for k in GAUSSIAN_KEYS],
+                                        lr=0.0, eps=1e-15)
         self.render = render
         self.gen = torch.Generator().manual_seed(seed)   # shared seed -> identical schedule on every rank
         self.step_idx = 0
@@ -184,7 +197,7 @@ class ShardedMapper:
 
     def accumulate(self, frame):
         """Local backward of one keyframe into the flat gradient bucket (no communication)."""
-        loss, radius = mapping_loss(self.params(), frame, self.render)
+        loss, radius = mapping_loss(self.params(), frame, self.render, fused_loss=self.fused)
         loss.backward()
         return loss.detach(), radius
 

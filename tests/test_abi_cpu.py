@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def _declared_symbols():
     text = open(os.path.join(ROOT, "include", "splatam_b200.h")).read()
-    return sorted(set(re.findall(r"SB_API\s+(?:const\s+char\*|int)\s+(sb_\w+)\s*\(", text)))
+    return sorted(set(re.findall(r"SB_API\s+(?:const\s+char\*|int|size_t)\s+(sb_\w+)\s*\(", text)))
 
 
 def test_library_exports_every_declared_symbol():
