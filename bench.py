@@ -231,7 +231,8 @@ def mapping_bench(dev, world, dist_on, impl, steps=8, warmup=3, P=1_000_000):
     frames = [dict(id=t, cam=cam, w2c=torch.eye(4, device=dev), im=torch.rand(3, sc.h, sc.w, generator=g).to(dev),
                    depth=(1.0 + 2.0 * torch.rand(1, sc.h, sc.w, generator=g)).to(dev)) for t in range(nframes)]
     render = (lambda settings, **rv: Rast(raster_settings=settings)(**rv))
-    mapper = M.ShardedMapper(gauss, rots.to(dev), trans.to(dev), render=render, seed=11)
+    # the reference arm keeps the stock PyTorch Adam / SSIM path: none of this repo's kernels on it
+    mapper = M.ShardedMapper(gauss, rots.to(dev), trans.to(dev), render=render, seed=11, fused=(impl == "ours"))
     ms = timed(lambda: mapper.step(frames), steps, warmup, dev, dist_on) / steps
     return dict(metric="mapping keyframe-iters/sec", value=world * 1000.0 / ms, unit="keyframe-iters/s",
                 ms_per_step=ms, keyframes_per_step=world, gaussians=P, width=sc.w, height=sc.h,
