@@ -168,6 +168,25 @@ SB_API int sb_image_loss_forward(const float* x, const float* y, int C, int H, i
 SB_API int sb_image_loss_backward(const float* x, const float* y, int C, int H, int W, const float* work,
                                   const float* grad_out, float w_ssim, float w_l1, float* grad_x, void* stream);
 
+/* ---- fused parameter glue ----------------------------------------------
+ * sb_prepare_forward: raw SplaTAM parameters + frame pose -> the operator's inputs, in one kernel
+ * (replaces transform_to_frame + transformed_params2rendervar + transformed_params2depthplussilhouette,
+ * R/utils/slam_helpers.py:124-139,196-304).  scale_dim = 1 (isotropic log_scales [P,1]) or 3.
+ * rel_w2c, w2c0: row-major 4x4; cam_rot: the normalised camera quaternion (w,x,y,z).
+ * sb_prepare_backward: gradients of the six outputs (any may be NULL = zero) -> gradients of the raw
+ * parameters; if want_pose, g_pose16 receives d/d rel_w2c[0:3,0:4] (12) then d/d cam_rot (4). */
+SB_API int sb_prepare_forward(int P, int scale_dim, const float* means3D, const float* unnorm_rotations,
+                              const float* logit_opacities, const float* log_scales, const float* rel_w2c,
+                              const float* cam_rot, const float* w2c0, float* means_cam, float* rotations,
+                              float* opacities, float* scales3, float* depth_sil_colors, void* stream);
+SB_API int sb_prepare_backward(int P, int scale_dim, int want_pose, const float* means3D,
+                               const float* unnorm_rotations, const float* rel_w2c, const float* cam_rot,
+                               const float* w2c0, const float* means_cam, const float* opacities,
+                               const float* scales3, const float* g_means_cam, const float* g_rotations,
+                               const float* g_opacities, const float* g_scales3, const float* g_depth_sil_colors,
+                               float* g_means3D, float* g_unnorm_rotations, float* g_logit_opacities,
+                               float* g_log_scales, float* g_pose16, void* stream);
+
 /* ---- per-stage device timing (measurement only; bench.py's roofline pass) -------------------
  * Between sb_profile_begin() and sb_profile_end() every stage launch of this process is bracketed
  * by CUDA events on its stream.  sb_profile_end synchronises, writes the summed milliseconds and call

@@ -84,6 +84,28 @@ def depth_sil_rendervar(params, w2c, tg):
                 means2D=torch.zeros_like(params["means3D"], requires_grad=True) + 0)
 
 
+def fused_rendervars(params, time_idx, w2c0, camera_grad):
+    """Both rendervars of one frame from ONE fused kernel (splatam_b200/prepare.py); equals
+    transform_to_frame + rgb_rendervar + depth_sil_rendervar above to float rounding."""
+    from .prepare import prepare_gaussians
+    rot, tran = params["cam_unnorm_rots"][..., time_idx], params["cam_trans"][..., time_idx]
+    if not camera_grad:
+        rot, tran = rot.detach(), tran.detach()
+    cam_rot = F.normalize(rot)
+    dev = params["means3D"].device
+    rel_w2c = torch.eye(4, device=dev, dtype=torch.float32)
+    rel_w2c[:3, :3] = build_rotation(cam_rot)
+    rel_w2c[:3, 3] = tran
+    means_cam, rots, opac, sc3, dcols = prepare_gaussians(params["means3D"], params["unnorm_rotations"],
+                                                          params["logit_opacities"], params["log_scales"], rel_w2c,
+                                                          cam_rot, w2c0)
+    z2 = lambda: torch.zeros_like(params["means3D"], requires_grad=True) + 0
+    rgb = dict(means3D=means_cam, colors_precomp=params["rgb_colors"], rotations=rots, opacities=opac, scales=sc3,
+               means2D=z2())
+    dep = dict(means3D=means_cam, colors_precomp=dcols, rotations=rots, opacities=opac, scales=sc3, means2D=z2())
+    return rgb, dep
+
+
 def _ssim_window(channel, device, size=11, sigma=1.5):
     g = torch.tensor([math.exp(-(x - size // 2) ** 2 / float(2 * sigma ** 2)) for x in range(size)])
     g = (g / g.sum()).unsqueeze(1)
@@ -108,9 +130,13 @@ def mapping_loss(params, frame, render, loss_weights=(0.5, 1.0), ignore_outlier_
     (R/scripts/splatam.py:214-347 with tracking=False, mapping=True, do_ba=False, use_l1=True).
     frame: dict(im [3,H,W], depth [1,H,W], cam settings, w2c [4,4] first-frame w2c, id time index).
     render(settings, **rendervar) -> (image, radii, depth)."""
-    tg = transform_to_frame(params, frame["id"], gaussians_grad=True, camera_grad=False)
-    im, radius, _ = render(frame["cam"], **rgb_rendervar(params, tg))
-    depth_sil, _, _ = render(frame["cam"], **depth_sil_rendervar(params, frame["w2c"], tg))
+    if fused_loss:      # fused glue: one kernel builds both rendervars (csrc/prepare.cu)
+        rv_rgb, rv_depth = fused_rendervars(params, frame["id"], frame["w2c"], camera_grad=False)
+    else:
+        tg = transform_to_frame(params, frame["id"], gaussians_grad=True, camera_grad=False)
+        rv_rgb, rv_depth = rgb_rendervar(params, tg), depth_sil_rendervar(params, frame["w2c"], tg)
+    im, radius, _ = render(frame["cam"], **rv_rgb)
+    depth_sil, _, _ = render(frame["cam"], **rv_depth)
     depth = depth_sil[0:1]
     uncertainty = (depth_sil[2:3] - depth ** 2).detach()
     mask = (frame["depth"] > 0) & (~torch.isnan(depth)) & (~torch.isnan(uncertainty))
@@ -118,7 +144,10 @@ def mapping_loss(params, frame, render, loss_weights=(0.5, 1.0), ignore_outlier_
         err = torch.abs(frame["depth"] - depth) * (frame["depth"] > 0)
         mask = mask & (err < 10 * err.median())
     mask = mask.detach()
-    l_depth = torch.abs(frame["depth"] - depth)[mask].mean()
+    if fused_loss:      # same value as [mask].mean() without the nonzero/index/sort kernels of boolean indexing
+        l_depth = (torch.abs(frame["depth"] - depth) * mask).sum() / mask.sum()
+    else:
+        l_depth = torch.abs(frame["depth"] - depth)[mask].mean()
     if fused_loss:      # one forward + one backward kernel instead of 5 depthwise convs + autograd (train_ops.cu)
         from .train_ops import image_loss
         l_im = image_loss(im, frame["im"], 0.8, 0.2)
