@@ -131,6 +131,28 @@ SB_API int sb_backward(const sb_settings* s, int P, int num_rendered,
                 float* dL_dcov3D,
                 void* stream);
 
+/* ---- fused two-colour-set render ---------------------------------------
+ * SplaTAM renders the SAME geometry twice per iteration with different colours_precomp: RGB and
+ * [depth, 1, depth^2] (R/scripts/splatam.py:249,253).  The _ex entry points blend both sets in one pass:
+ * one projection, one sort, one forward and one backward blend.  colors2 / out_color2 / dL_dout_color2 /
+ * dL_dcolors2 == NULL reduce them to the plain calls above.  Outputs of the first set are bit-identical
+ * to a plain render; dL_dmeans2D carries the FIRST set's share only (SplaTAM reads the means2D gradient
+ * of the RGB render, splatam.py:250), every other gradient is the sum over both sets.  Workspaces must be
+ * sized with the _ex size functions (color_sets = 2). */
+SB_API int sb_binning_workspace_bytes_ex(int num_rendered, int width, int height, int color_sets, size_t* bytes);
+SB_API int sb_backward_workspace_bytes_ex(int P, int color_sets, size_t* bytes);
+SB_API int sb_forward_render_ex(const sb_settings* s, int P, int num_rendered, const float* colors,
+                         const float* colors2, const void* geom_ws, size_t geom_ws_bytes, void* binning_ws,
+                         size_t binning_ws_bytes, void* image_ws, size_t image_ws_bytes, float* out_color,
+                         float* out_color2, float* out_depth, void* stream);
+SB_API int sb_backward_ex(const sb_settings* s, int P, int num_rendered, const float* means3D, const float* colors,
+                   const float* scales, const float* rotations, const float* cov3D_precomp, const int32_t* radii,
+                   const void* geom_ws, size_t geom_ws_bytes, const void* binning_ws, size_t binning_ws_bytes,
+                   const void* image_ws, size_t image_ws_bytes, void* bwd_ws, size_t bwd_ws_bytes,
+                   const float* dL_dout_color, const float* dL_dout_color2, float* dL_dmeans3D,
+                   float* dL_dmeans2D, float* dL_dcolors, float* dL_dcolors2, float* dL_dopacity,
+                   float* dL_dscales, float* dL_drotations, float* dL_dcov3D, void* stream);
+
 /* ---- markVisible (X/cuda_rasterizer/rasterizer_impl.cu:54-66,141-153) ------------------- */
 SB_API int sb_mark_visible(int P, const float* means3D, const float* viewmatrix,
                     const float* projmatrix, uint8_t* present, void* stream);

@@ -48,6 +48,13 @@ _SIGNATURES = {
                                  ctypes.POINTER(_i), _vp]),
     "sb_forward_render": (_i, [ctypes.POINTER(SbSettings), _i, _i, _vp, _vp, _sz, _vp, _sz, _vp, _sz,
                                _vp, _vp, _vp]),
+    "sb_binning_workspace_bytes_ex": (_i, [_i, _i, _i, _i, ctypes.POINTER(_sz)]),
+    "sb_backward_workspace_bytes_ex": (_i, [_i, _i, ctypes.POINTER(_sz)]),
+    "sb_forward_render_ex": (_i, [ctypes.POINTER(SbSettings), _i, _i, _vp, _vp, _vp, _sz, _vp, _sz, _vp, _sz,
+                                  _vp, _vp, _vp, _vp]),
+    "sb_backward_ex": (_i, [ctypes.POINTER(SbSettings), _i, _i, _vp, _vp, _vp, _vp, _vp, _vp,
+                            _vp, _sz, _vp, _sz, _vp, _sz, _vp, _sz,
+                            _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sb_backward": (_i, [ctypes.POINTER(SbSettings), _i, _i, _vp, _vp, _vp, _vp, _vp, _vp,
                          _vp, _sz, _vp, _sz, _vp, _sz, _vp, _sz,
                          _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

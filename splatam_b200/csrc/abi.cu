@@ -47,7 +47,7 @@ GeometryWs carve_geometry(void* ws, int P, size_t* total) {
     return g;
 }
 
-BinningWs carve_binning(void* ws, int R, int tiles, size_t* total) {
+BinningWs carve_binning(void* ws, int R, int tiles, int color_sets, size_t* total) {
     Carver c(ws);
     BinningWs b;
     const size_t n = (size_t)(R > 0 ? R : 1);
@@ -61,6 +61,7 @@ BinningWs carve_binning(void* ws, int R, int tiles, size_t* total) {
     b.recC = c.take<float4>(n);
     b.cub_temp_bytes = binning_cub_temp_bytes((int)n, keys16);
     b.cub_temp = c.take<char>(b.cub_temp_bytes);
+    b.recD = color_sets > 1 ? c.take<float4>(n) : nullptr;   // after everything else: the 1-set layout is a prefix
     if (total) *total = c.used();
     return b;
 }
@@ -137,17 +138,22 @@ SB_API int sb_image_workspace_bytes(int width, int height, size_t* bytes) {
     carve_image(nullptr, width, height, bytes);
     return SB_OK;
 }
-SB_API int sb_binning_workspace_bytes(int num_rendered, int width, int height, size_t* bytes) {
-    if (num_rendered < 0 || width <= 0 || height <= 0 || !bytes) return SB_ERR_BAD_ARG;
+SB_API int sb_binning_workspace_bytes_ex(int num_rendered, int width, int height, int color_sets, size_t* bytes) {
+    if (num_rendered < 0 || width <= 0 || height <= 0 || !bytes || color_sets < 1 || color_sets > 2) return SB_ERR_BAD_ARG;
     const int tiles = ((width + kTile - 1) / kTile) * ((height + kTile - 1) / kTile);
-    carve_binning(nullptr, num_rendered, tiles, bytes);
+    carve_binning(nullptr, num_rendered, tiles, color_sets, bytes);
     return SB_OK;
 }
-SB_API int sb_backward_workspace_bytes(int P, size_t* bytes) {
-    if (P < 0 || !bytes) return SB_ERR_BAD_ARG;
-    *bytes = ((size_t)(P > 0 ? P : 1) * kAccumStride * sizeof(float) + kAlign - 1) / kAlign * kAlign;
+SB_API int sb_binning_workspace_bytes(int num_rendered, int width, int height, size_t* bytes) {
+    return sb_binning_workspace_bytes_ex(num_rendered, width, height, 1, bytes);
+}
+SB_API int sb_backward_workspace_bytes_ex(int P, int color_sets, size_t* bytes) {
+    if (P < 0 || !bytes || color_sets < 1 || color_sets > 2) return SB_ERR_BAD_ARG;
+    const int stride = color_sets > 1 ? kAccumStride2 : kAccumStride;
+    *bytes = ((size_t)(P > 0 ? P : 1) * stride * sizeof(float) + kAlign - 1) / kAlign * kAlign;
     return SB_OK;
 }
+SB_API int sb_backward_workspace_bytes(int P, size_t* bytes) { return sb_backward_workspace_bytes_ex(P, 1, bytes); }
 
 SB_API int sb_forward_geometry(const sb_settings* s, int P, const float* means3D, const float* opacities,
                         const float* scales, const float* rotations, const float* cov3D_precomp,
@@ -177,20 +183,30 @@ SB_API int sb_forward_geometry(const sb_settings* s, int P, const float* means3D
 SB_API int sb_forward_render(const sb_settings* s, int P, int num_rendered, const float* colors,
                       const void* geom_ws, size_t geom_ws_bytes, void* binning_ws, size_t binning_ws_bytes,
                       void* image_ws, size_t image_ws_bytes, float* out_color, float* out_depth, void* stream) {
+    return sb_forward_render_ex(s, P, num_rendered, colors, nullptr, geom_ws, geom_ws_bytes, binning_ws,
+                                binning_ws_bytes, image_ws, image_ws_bytes, out_color, nullptr, out_depth, stream);
+}
+
+SB_API int sb_forward_render_ex(const sb_settings* s, int P, int num_rendered, const float* colors,
+                         const float* colors2, const void* geom_ws, size_t geom_ws_bytes, void* binning_ws,
+                         size_t binning_ws_bytes, void* image_ws, size_t image_ws_bytes, float* out_color,
+                         float* out_color2, float* out_depth, void* stream) {
     if (!settings_ok(s) || P < 0 || num_rendered < 0 || !image_ws || !out_color || !out_depth) return SB_ERR_BAD_ARG;
     if (P > 0 && (!colors || !geom_ws)) return SB_ERR_BAD_ARG;
+    if ((colors2 != nullptr) != (out_color2 != nullptr)) return SB_ERR_BAD_ARG;
+    const int sets = colors2 ? 2 : 1;
     if (num_rendered > 0 && !binning_ws) return SB_ERR_BAD_ARG;
     size_t need = 0;
     GeometryWs g = carve_geometry(const_cast<void*>(geom_ws), P, &need);
     if (P > 0 && geom_ws_bytes < need) return SB_ERR_WORKSPACE;
-    BinningWs b = carve_binning(binning_ws, num_rendered, tiles_of(s), &need);
+    BinningWs b = carve_binning(binning_ws, num_rendered, tiles_of(s), sets, &need);
     if (num_rendered > 0 && binning_ws_bytes < need) return SB_ERR_WORKSPACE;
     ImageWs img = carve_image(image_ws, s->image_width, s->image_height, &need);
     if (image_ws_bytes < need) return SB_ERR_WORKSPACE;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    int rc = launch_binning(*s, P, num_rendered, colors, g, b, img, st);
+    int rc = launch_binning(*s, P, num_rendered, colors, colors2, g, b, img, st);
     if (rc != SB_OK) return rc;
-    return launch_blend_forward(*s, num_rendered, g, b, img, out_color, out_depth, st);
+    return launch_blend_forward(*s, num_rendered, g, b, img, out_color, out_color2, out_depth, st);
 }
 
 SB_API int sb_backward(const sb_settings* s, int P, int num_rendered, const float* means3D, const float* colors,
@@ -199,7 +215,23 @@ SB_API int sb_backward(const sb_settings* s, int P, int num_rendered, const floa
                 const void* image_ws, size_t image_ws_bytes, void* bwd_ws, size_t bwd_ws_bytes,
                 const float* dL_dout_color, float* dL_dmeans3D, float* dL_dmeans2D, float* dL_dcolors,
                 float* dL_dopacity, float* dL_dscales, float* dL_drotations, float* dL_dcov3D, void* stream) {
+    return sb_backward_ex(s, P, num_rendered, means3D, colors, scales, rotations, cov3D_precomp, radii, geom_ws,
+                          geom_ws_bytes, binning_ws, binning_ws_bytes, image_ws, image_ws_bytes, bwd_ws, bwd_ws_bytes,
+                          dL_dout_color, nullptr, dL_dmeans3D, dL_dmeans2D, dL_dcolors, nullptr, dL_dopacity,
+                          dL_dscales, dL_drotations, dL_dcov3D, stream);
+}
+
+SB_API int sb_backward_ex(const sb_settings* s, int P, int num_rendered, const float* means3D, const float* colors,
+                   const float* scales, const float* rotations, const float* cov3D_precomp, const int32_t* radii,
+                   const void* geom_ws, size_t geom_ws_bytes, const void* binning_ws, size_t binning_ws_bytes,
+                   const void* image_ws, size_t image_ws_bytes, void* bwd_ws, size_t bwd_ws_bytes,
+                   const float* dL_dout_color, const float* dL_dout_color2, float* dL_dmeans3D,
+                   float* dL_dmeans2D, float* dL_dcolors, float* dL_dcolors2, float* dL_dopacity,
+                   float* dL_dscales, float* dL_drotations, float* dL_dcov3D, void* stream) {
     (void)geom_ws; (void)geom_ws_bytes;
+    if ((dL_dout_color2 != nullptr) != (dL_dcolors2 != nullptr)) return SB_ERR_BAD_ARG;
+    const int sets = dL_dout_color2 ? 2 : 1;
+    const int stride = sets > 1 ? kAccumStride2 : kAccumStride;
     if (!settings_ok(s) || P < 0 || num_rendered < 0) return SB_ERR_BAD_ARG;
     if (P == 0) return SB_OK;
     if (!means3D || !colors || !radii || !image_ws || !bwd_ws || !dL_dout_color || !dL_dmeans3D ||
@@ -208,20 +240,20 @@ SB_API int sb_backward(const sb_settings* s, int P, int num_rendered, const floa
     if (!cov3D_precomp && (!scales || !rotations || !dL_dscales || !dL_drotations)) return SB_ERR_BAD_ARG;
     if (num_rendered > 0 && !binning_ws) return SB_ERR_BAD_ARG;
     size_t need = 0;
-    BinningWs b = carve_binning(const_cast<void*>(binning_ws), num_rendered, tiles_of(s), &need);
+    BinningWs b = carve_binning(const_cast<void*>(binning_ws), num_rendered, tiles_of(s), sets, &need);
     if (num_rendered > 0 && binning_ws_bytes < need) return SB_ERR_WORKSPACE;
     ImageWs img = carve_image(const_cast<void*>(image_ws), s->image_width, s->image_height, &need);
     if (image_ws_bytes < need) return SB_ERR_WORKSPACE;
-    sb_backward_workspace_bytes(P, &need);
+    sb_backward_workspace_bytes_ex(P, sets, &need);
     if (bwd_ws_bytes < need) return SB_ERR_WORKSPACE;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     float* accum = static_cast<float*>(bwd_ws);
     { ScopedStage _p(kStAccumZero, st);
-      SB_CUDA_CHECK(cudaMemsetAsync(accum, 0, (size_t)P * kAccumStride * sizeof(float), st)); }
-    int rc = launch_blend_backward(*s, num_rendered, b, img, dL_dout_color, accum, st);
+      SB_CUDA_CHECK(cudaMemsetAsync(accum, 0, (size_t)P * stride * sizeof(float), st)); }
+    int rc = launch_blend_backward(*s, num_rendered, b, img, dL_dout_color, dL_dout_color2, accum, st);
     if (rc != SB_OK) return rc;
-    return launch_geometry_backward(*s, P, means3D, colors, scales, rotations, cov3D_precomp, radii, accum,
-                                    dL_dmeans3D, dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dscales,
+    return launch_geometry_backward(*s, P, means3D, colors, scales, rotations, cov3D_precomp, radii, accum, stride,
+                                    dL_dmeans3D, dL_dmeans2D, dL_dcolors, dL_dcolors2, dL_dopacity, dL_dscales,
                                     dL_drotations, dL_dcov3D, st);
 }
 
@@ -255,7 +287,7 @@ SB_API int sb_export_binning(const sb_settings* s, int P, int num_rendered, cons
     GeometryWs g = carve_geometry(const_cast<void*>(geom_ws), P, &need);
     if (geom_ws_bytes < need) return SB_ERR_WORKSPACE;
     const int tiles = tiles_of(s);
-    BinningWs b = carve_binning(const_cast<void*>(binning_ws), num_rendered, tiles, &need);
+    BinningWs b = carve_binning(const_cast<void*>(binning_ws), num_rendered, tiles, 1, &need);
     if (num_rendered > 0 && (!binning_ws || binning_ws_bytes < need)) return SB_ERR_WORKSPACE;
     ImageWs img = carve_image(const_cast<void*>(image_ws), s->image_width, s->image_height, &need);
     if (image_ws_bytes < need) return SB_ERR_WORKSPACE;

@@ -42,8 +42,9 @@ template <typename KeyT>
 __global__ void __launch_bounds__(256)
 ranges_and_records_kernel(int R, const KeyT* __restrict__ tile_sorted, const uint32_t* __restrict__ point_list,
                           const float4* __restrict__ geomA, const float4* __restrict__ geomB,
-                          const float* __restrict__ colors, uint2* __restrict__ ranges,
-                          float4* __restrict__ recA, float4* __restrict__ recB, float4* __restrict__ recC) {
+                          const float* __restrict__ colors, const float* __restrict__ colors2,
+                          uint2* __restrict__ ranges, float4* __restrict__ recA, float4* __restrict__ recB,
+                          float4* __restrict__ recC, float4* __restrict__ recD) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= R) return;
     const uint32_t tile = tile_sorted[i];
@@ -58,11 +59,15 @@ ranges_and_records_kernel(int R, const KeyT* __restrict__ tile_sorted, const uin
     recB[i] = __ldg(geomB + g);
     const float* c = colors + 3 * (size_t)g;
     recC[i] = make_float4(__ldg(c), __ldg(c + 1), __ldg(c + 2), __uint_as_float(g));
+    if (colors2 != nullptr) {
+        const float* e = colors2 + 3 * (size_t)g;
+        recD[i] = make_float4(__ldg(e), __ldg(e + 1), __ldg(e + 2), 0.f);
+    }
 }
 
 template <typename KeyT>
-int run_binning(const sb_settings& s, int P, int R, int bits, const float* colors, const GeometryWs& g,
-                const BinningWs& b, const ImageWs& img, cudaStream_t st) {
+int run_binning(const sb_settings& s, int P, int R, int bits, const float* colors, const float* colors2,
+                const GeometryWs& g, const BinningWs& b, const ImageWs& img, cudaStream_t st) {
     const uint32_t gx = (s.image_width + kTile - 1) / kTile;
     KeyT* tile_unsorted = reinterpret_cast<KeyT*>(b.tile_unsorted);
     KeyT* tile_sorted = reinterpret_cast<KeyT*>(b.tile_sorted);
@@ -77,8 +82,8 @@ int run_binning(const sb_settings& s, int P, int R, int bits, const float* color
                                                     b.point_list, R, 0, bits, st)); }
     ScopedStage _p(kStRecords, st);
     ranges_and_records_kernel<KeyT><<<(R + 255) / 256, 256, 0, st>>>(R, tile_sorted, b.point_list, g.geomA,
-                                                                     g.geomB, colors, img.ranges, b.recA,
-                                                                     b.recB, b.recC);
+                                                                     g.geomB, colors, colors2, img.ranges,
+                                                                     b.recA, b.recB, b.recC, b.recD);
     SB_LAUNCH_CHECK("ranges_and_records_kernel");
     return SB_OK;
 }
@@ -96,15 +101,15 @@ size_t binning_cub_temp_bytes(int R, bool keys16) {
     return bytes;
 }
 
-int launch_binning(const sb_settings& s, int P, int R, const float* colors, const GeometryWs& g,
-                   const BinningWs& b, const ImageWs& img, cudaStream_t st) {
+int launch_binning(const sb_settings& s, int P, int R, const float* colors, const float* colors2,
+                   const GeometryWs& g, const BinningWs& b, const ImageWs& img, cudaStream_t st) {
     const int gx = (s.image_width + kTile - 1) / kTile, gy = (s.image_height + kTile - 1) / kTile;
     const int tiles = gx * gy;
     SB_CUDA_CHECK(cudaMemsetAsync(img.ranges, 0, sizeof(uint2) * (size_t)tiles, st));  // rasterizer_impl.cu:311
     if (R <= 0) return SB_OK;
     const int bits = (int)higher_msb((uint32_t)tiles);  // same bit count as the reference sort uses
-    if (bits <= 16) return run_binning<uint16_t>(s, P, R, bits, colors, g, b, img, st);
-    return run_binning<uint32_t>(s, P, R, bits, colors, g, b, img, st);
+    if (bits <= 16) return run_binning<uint16_t>(s, P, R, bits, colors, colors2, g, b, img, st);
+    return run_binning<uint32_t>(s, P, R, bits, colors, colors2, g, b, img, st);
 }
 
 }  // namespace sb

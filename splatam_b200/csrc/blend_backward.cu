@@ -31,11 +31,14 @@ constexpr int kBlendThreads = (kConsumerWarps + 1) * 32;
 constexpr int kQStride = 33;      // row stride of the queue in floats: conflict-free for both phases
 
 // kQueue = queued survivors per warp before phase 2 runs (16: two lanes per Gaussian, 8: four lanes)
-template <int kQueue>
+// NCH = 3 (reference operator) or 6 (fused two-colour-set render; the first set's share of dL/dmean2D is
+// tracked separately because SplaTAM reads the means2D gradient of the RGB render only, splatam.py:250)
+template <int NCH, int kQueue>
 struct __align__(128) BwdSmem {
     float4 A[kStages][kBatch];
     float4 B[kStages][kBatch];
     float4 C[kStages][kBatch];
+    float4 D[NCH == 6 ? kStages : 1][NCH == 6 ? kBatch : 1];
     uint64_t full[kStages];
     uint64_t empty[kStages];
     uint32_t nmax;
@@ -43,7 +46,8 @@ struct __align__(128) BwdSmem {
     float4 meta[kConsumerWarps][kQueue][2];       // {gx-x0, gy-y0, conic.x, conic.y}, {conic.z, opacity, bits(id), -}
     float qw[kConsumerWarps][kQueue][kQStride];   // w  = G * dL/dG      per (slot, pixel)
     float qc[kConsumerWarps][kQueue][kQStride];   // ca = alpha * T      per (slot, pixel)
-    float dL[kConsumerWarps][3][32];              // dL/dpixel of the warp's 32 pixels
+    float qr[NCH == 6 ? kConsumerWarps : 1][NCH == 6 ? kQueue : 1][kQStride];   // w of the first colour set only
+    float dL[kConsumerWarps][NCH][32];            // dL/dpixel of the warp's 32 pixels
 };
 
 // 1/x for x in [0.01, 1]: MUFU.RCP + one Newton step (error < 1 ulp; the reference divides, IEEE).
@@ -62,9 +66,10 @@ __device__ __forceinline__ void sts_v4(uint32_t addr, float a, float b, float c,
 
 // Phase 2: lanes (s, part) = (lane % kQueue, lane / kQueue) sweep pixels [kQueue*part, kQueue*(part+1))
 // of queue slot s (kQueue pixels per lane, 32/kQueue lanes per queued Gaussian).
-template <int kQueue>
-__device__ __forceinline__ void flush_queue(BwdSmem<kQueue>& sm, int warp, int lane, int count, float ddelx_dx,
+template <int NCH, int kQueue>
+__device__ __forceinline__ void flush_queue(BwdSmem<NCH, kQueue>& sm, int warp, int lane, int count, float ddelx_dx,
                                             float ddely_dy, float* __restrict__ accum) {
+    constexpr int kStride = NCH == 6 ? kAccumStride2 : kAccumStride;
     __syncwarp();
     const int s = lane % kQueue, part = lane / kQueue;
     const float4 m0 = sm.meta[warp][s][0], m1 = sm.meta[warp][s][1];
@@ -75,6 +80,7 @@ __device__ __forceinline__ void flush_queue(BwdSmem<kQueue>& sm, int warp, int l
     const float* d1 = &sm.dL[warp][1][kQueue * part];
     const float* d2 = &sm.dL[warp][2][kQueue * part];
     float Sw = 0.f, Swx = 0.f, Swy = 0.f, Sxx = 0.f, Sxy = 0.f, Syy = 0.f, C0 = 0.f, C1 = 0.f, C2 = 0.f;
+    float E0 = 0.f, E1 = 0.f, E2 = 0.f, Rx = 0.f, Ry = 0.f;   // NCH == 6 only
 #pragma unroll
     for (int it = 0; it < kQueue; ++it) {
         const float w = qw[it], ca = qc[it];
@@ -83,6 +89,13 @@ __device__ __forceinline__ void flush_queue(BwdSmem<kQueue>& sm, int warp, int l
         Sw += w; Swx += wdx; Swy += wdy;
         Sxx = fmaf(wdx, dx, Sxx); Sxy = fmaf(wdx, dy, Sxy); Syy = fmaf(wdy, dy, Syy);
         C0 = fmaf(ca, d0[it], C0); C1 = fmaf(ca, d1[it], C1); C2 = fmaf(ca, d2[it], C2);
+        if (NCH == 6) {
+            const float wr = sm.qr[warp][s][kQueue * part + it];
+            Rx = fmaf(wr, dx, Rx); Ry = fmaf(wr, dy, Ry);
+            E0 = fmaf(ca, sm.dL[warp][NCH - 3][kQueue * part + it], E0);
+            E1 = fmaf(ca, sm.dL[warp][NCH - 2][kQueue * part + it], E1);
+            E2 = fmaf(ca, sm.dL[warp][NCH - 1][kQueue * part + it], E2);
+        }
     }
     constexpr uint32_t full = 0xffffffffu;
 #pragma unroll
@@ -92,11 +105,16 @@ __device__ __forceinline__ void flush_queue(BwdSmem<kQueue>& sm, int warp, int l
         Sxy += __shfl_xor_sync(full, Sxy, off); Syy += __shfl_xor_sync(full, Syy, off);
         C0 += __shfl_xor_sync(full, C0, off);   C1 += __shfl_xor_sync(full, C1, off);
         C2 += __shfl_xor_sync(full, C2, off);
+        if (NCH == 6) {
+            E0 += __shfl_xor_sync(full, E0, off); E1 += __shfl_xor_sync(full, E1, off);
+            E2 += __shfl_xor_sync(full, E2, off); Rx += __shfl_xor_sync(full, Rx, off);
+            Ry += __shfl_xor_sync(full, Ry, off);
+        }
     }
     if (lane < count) {
         // dG/ddelx = -G (dx a + dy b), dG/ddely = -G (dy c + dx b)   (backward.cu:539-546)
         const float a = m0.z, b = m0.w, c = m1.x, op = m1.y;
-        float* row = accum + (size_t)__float_as_uint(m1.z) * kAccumStride;
+        float* row = accum + (size_t)__float_as_uint(m1.z) * kStride;
         atomicAdd(row + 0, -(a * Swx + b * Swy) * ddelx_dx);
         atomicAdd(row + 1, -(c * Swy + b * Swx) * ddely_dy);
         atomicAdd(row + 2, -0.5f * Sxx);
@@ -106,19 +124,26 @@ __device__ __forceinline__ void flush_queue(BwdSmem<kQueue>& sm, int warp, int l
         atomicAdd(row + 6, C0);
         atomicAdd(row + 7, C1);
         atomicAdd(row + 8, C2);
+        if (NCH == 6) {
+            atomicAdd(row + 9, E0); atomicAdd(row + 10, E1); atomicAdd(row + 11, E2);
+            atomicAdd(row + 12, -(a * Rx + b * Ry) * ddelx_dx);
+            atomicAdd(row + 13, -(c * Ry + b * Rx) * ddely_dy);
+        }
     }
     __syncwarp();
 }
 
-template <int kQueue, int kMinBlocks>
+template <int NCH, int kQueue, int kMinBlocks>
 __global__ void __launch_bounds__(kBlendThreads, kMinBlocks)
 blend_backward_kernel(const uint2* __restrict__ ranges, const float4* __restrict__ recA,
                       const float4* __restrict__ recB, const float4* __restrict__ recC,
+                      const float4* __restrict__ recD,
                       int W, int H, uint32_t grid_x, const float* __restrict__ bg,
                       const float* __restrict__ final_T, const uint32_t* __restrict__ n_contrib,
-                      const float* __restrict__ dL_dpix, float* __restrict__ accum) {
+                      const float* __restrict__ dL_dpix, const float* __restrict__ dL_dpix2,
+                      float* __restrict__ accum) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    BwdSmem<kQueue>& sm = *reinterpret_cast<BwdSmem<kQueue>*>(smem_raw);
+    BwdSmem<NCH, kQueue>& sm = *reinterpret_cast<BwdSmem<NCH, kQueue>*>(smem_raw);
     const uint32_t tile = blockIdx.x;
     const uint2 range = ranges[tile];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -140,8 +165,13 @@ blend_backward_kernel(const uint2* __restrict__ ranges, const float4* __restrict
     const uint32_t warp_nc = __reduce_max_sync(0xffffffffu, nc);
     if (lane == 0 && warp_nc > 0u) atomicMax(&sm.nmax, warp_nc);
     float dL0 = 0.f, dL1 = 0.f, dL2 = 0.f;
+    float dL3 = 0.f, dL4 = 0.f, dL5 = 0.f;
     if (inside) { dL0 = dL_dpix[pix]; dL1 = dL_dpix[hw + pix]; dL2 = dL_dpix[2 * hw + pix]; }
-    if (warp < kConsumerWarps) { sm.dL[warp][0][lane] = dL0; sm.dL[warp][1][lane] = dL1; sm.dL[warp][2][lane] = dL2; }
+    if (NCH == 6 && inside) { dL3 = dL_dpix2[pix]; dL4 = dL_dpix2[hw + pix]; dL5 = dL_dpix2[2 * hw + pix]; }
+    if (warp < kConsumerWarps) {
+        sm.dL[warp][0][lane] = dL0; sm.dL[warp][1][lane] = dL1; sm.dL[warp][2][lane] = dL2;
+        if (NCH == 6) { sm.dL[warp][NCH - 3][lane] = dL3; sm.dL[warp][NCH - 2][lane] = dL4; sm.dL[warp][NCH - 1][lane] = dL5; }
+    }
     __syncthreads();
     const int m = (int)sm.nmax;                 // entries [0, m) of the tile list can matter
     const int nb = (m + kBatch - 1) / kBatch;
@@ -154,10 +184,11 @@ blend_backward_kernel(const uint2* __restrict__ ranges, const float4* __restrict
                 const int hi = m - k * kBatch, cnt = min(kBatch, hi), lo = hi - cnt;
                 const uint32_t bytes = (uint32_t)cnt * 16u;
                 const size_t src = (size_t)range.x + (size_t)lo;
-                mbar_arrive_expect_tx(&sm.full[s], 3u * bytes);
+                mbar_arrive_expect_tx(&sm.full[s], (NCH == 6 ? 4u : 3u) * bytes);
                 tma_load_1d(sm.A[s], recA + src, bytes, &sm.full[s]);
                 tma_load_1d(sm.B[s], recB + src, bytes, &sm.full[s]);
                 tma_load_1d(sm.C[s], recC + src, bytes, &sm.full[s]);
+                if (NCH == 6) tma_load_1d(sm.D[s], recD + src, bytes, &sm.full[s]);
             }
         }
         return;
@@ -166,6 +197,8 @@ blend_backward_kernel(const uint2* __restrict__ ranges, const float4* __restrict
     const float pxf = (float)px, pyf = (float)py;
     const float fx0 = (float)x0, fx1 = (float)(x0 + 7), fy0 = (float)y0, fy1 = (float)(y0 + 3);
     const float bg_dot = __ldg(bg) * dL0 + __ldg(bg + 1) * dL1 + __ldg(bg + 2) * dL2;
+    const float bg_dot2 = NCH == 6 ? __ldg(bg) * dL3 + __ldg(bg + 1) * dL4 + __ldg(bg + 2) * dL5 : 0.f;
+    float acc3 = 0.f, acc4 = 0.f, acc5 = 0.f, lc3 = 0.f, lc4 = 0.f, lc5 = 0.f;   // second colour set
     const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;  // pixel -> NDC (backward.cu:452-453)
     float T = T_final;
     float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;          // accum_rec
@@ -175,6 +208,7 @@ blend_backward_kernel(const uint2* __restrict__ ranges, const float4* __restrict
     // keeps the generic->shared window arithmetic out of the inner loop)
     const uint32_t qw_lane = smem_u32(&sm.qw[warp][0][lane]);
     const uint32_t qc_lane = smem_u32(&sm.qc[warp][0][lane]);
+    const uint32_t qr_lane = smem_u32(&sm.qr[NCH == 6 ? warp : 0][0][lane]);
     const uint32_t meta_row = smem_u32(&sm.meta[warp][0][0]);
     uint32_t qoff = 0;                                 // qn * kQStride * 4
 
@@ -205,7 +239,7 @@ blend_backward_kernel(const uint2* __restrict__ ranges, const float4* __restrict
                     const bool active = ((uint32_t)(lo + j) < nc) && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
                     if (!__any_sync(0xffffffffu, active)) continue;
                     const float4 col = sm.C[s][j];
-                    float w = 0.f, ca = 0.f;
+                    float w = 0.f, ca = 0.f, wr = 0.f;
                     if (active) {
                         const float ir = fast_rcp(1.f - alpha);
                         T = T * ir;
@@ -217,18 +251,30 @@ blend_backward_kernel(const uint2* __restrict__ ranges, const float4* __restrict
                         lc0 = col.x; lc1 = col.y; lc2 = col.z;
                         float dL_dalpha = (col.x - acc0) * dL0 + (col.y - acc1) * dL1 + (col.z - acc2) * dL2;
                         dL_dalpha = fmaf(dL_dalpha, T, -(T_final * ir) * bg_dot);
-                        last_alpha = alpha;
                         w = G * (q.w * dL_dalpha);
+                        if (NCH == 6) {
+                            const float4 ex = sm.D[s][j];
+                            acc3 = fmaf(last_alpha, lc3, om * acc3);
+                            acc4 = fmaf(last_alpha, lc4, om * acc4);
+                            acc5 = fmaf(last_alpha, lc5, om * acc5);
+                            lc3 = ex.x; lc4 = ex.y; lc5 = ex.z;
+                            float d2 = (ex.x - acc3) * dL3 + (ex.y - acc4) * dL4 + (ex.z - acc5) * dL5;
+                            d2 = fmaf(d2, T, -(T_final * ir) * bg_dot2);
+                            wr = w;
+                            w = fmaf(G, q.w * d2, w);
+                        }
+                        last_alpha = alpha;
                     }
                     sts_f32(qw_lane + qoff, w);
                     sts_f32(qc_lane + qoff, ca);
+                    if (NCH == 6) sts_f32(qr_lane + qoff, wr);
                     if (lane == 0) {
                         sts_v4(meta_row + qn * 32, a.x - fx0, a.y - fy0, q.x, q.y);
                         sts_v4(meta_row + qn * 32 + 16, q.z, q.w, col.w, 0.f);
                     }
                     qoff += kQStride * 4;
                     if (++qn == kQueue) {
-                        flush_queue<kQueue>(sm, warp, lane, kQueue, ddelx_dx, ddely_dy, accum);
+                        flush_queue<NCH, kQueue>(sm, warp, lane, kQueue, ddelx_dx, ddely_dy, accum);
                         qn = 0; qoff = 0;
                     }
                 }
@@ -238,31 +284,29 @@ blend_backward_kernel(const uint2* __restrict__ ranges, const float4* __restrict
         if (lane == 0) mbar_arrive(&sm.empty[s]);
     }
     // rows >= qn hold stale data; flush_queue only writes rows < qn
-    if (qn > 0) flush_queue<kQueue>(sm, warp, lane, qn, ddelx_dx, ddely_dy, accum);
+    if (qn > 0) flush_queue<NCH, kQueue>(sm, warp, lane, qn, ddelx_dx, ddely_dy, accum);
 }
 
 }  // namespace
 
 int launch_blend_backward(const sb_settings& s, int R, const BinningWs& b, const ImageWs& img,
-                          const float* dL_dout_color, float* accum, cudaStream_t st) {
+                          const float* dL_dout_color, const float* dL_dout_color2, float* accum,
+                          cudaStream_t st) {
     if (R <= 0) return SB_OK;
     const int W = s.image_width, H = s.image_height;
     const uint32_t gx = (W + kTile - 1) / kTile, gy = (H + kTile - 1) / kTile;
-    static const int variant = [] { const char* e = getenv("SB_BWD_VARIANT"); return e ? atoi(e) : 0; }();
-#define SB_LAUNCH_BWD(Q, MB)                                                                                   \
-    do {                                                                                                       \
-        SB_CUDA_CHECK(cudaFuncSetAttribute(blend_backward_kernel<Q, MB>,                                       \
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BwdSmem<Q>))); \
-        ScopedStage _p(kStBlendBwd, st);                                                                       \
-        blend_backward_kernel<Q, MB><<<gx * gy, kBlendThreads, sizeof(BwdSmem<Q>), st>>>(                      \
-            img.ranges, b.recA, b.recB, b.recC, W, H, gx, s.bg, img.final_T, img.n_contrib, dL_dout_color, accum); \
+#define SB_LAUNCH_BWD(NCH, Q, MB)                                                                               \
+    do {                                                                                                        \
+        SB_CUDA_CHECK(cudaFuncSetAttribute(blend_backward_kernel<NCH, Q, MB>,                                   \
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize,                         \
+                                           (int)sizeof(BwdSmem<NCH, Q>)));                                      \
+        ScopedStage _p(kStBlendBwd, st);                                                                        \
+        blend_backward_kernel<NCH, Q, MB><<<gx * gy, kBlendThreads, sizeof(BwdSmem<NCH, Q>), st>>>(             \
+            img.ranges, b.recA, b.recB, b.recC, b.recD, W, H, gx, s.bg, img.final_T, img.n_contrib, dL_dout_color, \
+            dL_dout_color2, accum);                                                                             \
     } while (0)
-    switch (variant) {
-        case 1: SB_LAUNCH_BWD(8, 4); break;
-        case 2: SB_LAUNCH_BWD(16, 2); break;
-        case 3: SB_LAUNCH_BWD(8, 3); break;
-        default: SB_LAUNCH_BWD(16, 3); break;
-    }
+    if (dL_dout_color2 != nullptr) SB_LAUNCH_BWD(6, 8, 3);
+    else SB_LAUNCH_BWD(3, 16, 3);
 #undef SB_LAUNCH_BWD
     SB_LAUNCH_CHECK("blend_backward_kernel");
     return SB_OK;

@@ -26,23 +26,29 @@ constexpr int kStages = 4;
 constexpr int kConsumerWarps = 8;
 constexpr int kBlendThreads = (kConsumerWarps + 1) * 32;
 
+// NCH = 3: one colour set (the reference operator).  NCH = 6: two colour sets blended in one pass over
+// the same geometry (SplaTAM's RGB render + depth/silhouette render, R/scripts/splatam.py:249,253).
+template <int NCH>
 struct __align__(128) FwdSmem {
     float4 A[kStages][kBatch];
     float4 B[kStages][kBatch];
     float4 C[kStages][kBatch];
+    float4 D[NCH == 6 ? kStages : 1][NCH == 6 ? kBatch : 1];
     uint64_t full[kStages];
     uint64_t empty[kStages];
 };
 
-template <int kMinBlocks>
+template <int NCH, int kMinBlocks>
 __global__ void __launch_bounds__(kBlendThreads, kMinBlocks)
 blend_forward_kernel(const uint2* __restrict__ ranges, const float4* __restrict__ recA,
                      const float4* __restrict__ recB, const float4* __restrict__ recC,
+                     const float4* __restrict__ recD,
                      const uint32_t* __restrict__ depth_key, int W, int H, uint32_t grid_x,
                      const float* __restrict__ bg, float* __restrict__ out_color,
+                     float* __restrict__ out_color2,
                      float* __restrict__ out_depth, float* __restrict__ final_T,
                      uint32_t* __restrict__ n_contrib) {
-    __shared__ FwdSmem sm;
+    __shared__ FwdSmem<NCH> sm;
     const uint32_t tile = blockIdx.x;
     const uint2 range = ranges[tile];
     const int n = (int)(range.y - range.x);
@@ -64,10 +70,11 @@ blend_forward_kernel(const uint2* __restrict__ ranges, const float4* __restrict_
                 const int cnt = min(kBatch, n - k * kBatch);
                 const uint32_t bytes = (uint32_t)cnt * 16u;
                 const size_t src = (size_t)range.x + (size_t)k * kBatch;
-                mbar_arrive_expect_tx(&sm.full[s], 3u * bytes);
+                mbar_arrive_expect_tx(&sm.full[s], (NCH == 6 ? 4u : 3u) * bytes);
                 tma_load_1d(sm.A[s], recA + src, bytes, &sm.full[s]);
                 tma_load_1d(sm.B[s], recB + src, bytes, &sm.full[s]);
                 tma_load_1d(sm.C[s], recC + src, bytes, &sm.full[s]);
+                if (NCH == 6) tma_load_1d(sm.D[s], recD + src, bytes, &sm.full[s]);
             }
         }
         return;
@@ -81,7 +88,7 @@ blend_forward_kernel(const uint2* __restrict__ ranges, const float4* __restrict_
     const float pxf = (float)px, pyf = (float)py;
     const float fx0 = (float)x0, fx1 = (float)(x0 + 7), fy0 = (float)y0, fy1 = (float)(y0 + 3);
 
-    float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f;
+    float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f, E0 = 0.f, E1 = 0.f, E2 = 0.f;
     float D = 15.0f;  // median depth default (forward.cu:308)
     uint32_t last = 0;
     bool done = !inside;
@@ -120,6 +127,12 @@ blend_forward_kernel(const uint2* __restrict__ ranges, const float4* __restrict_
                                     C0 = __fmaf_rn(T, __fmul_rn(alpha, col.x), C0);
                                     C1 = __fmaf_rn(T, __fmul_rn(alpha, col.y), C1);
                                     C2 = __fmaf_rn(T, __fmul_rn(alpha, col.z), C2);
+                                    if (NCH == 6) {
+                                        const float4 ex = sm.D[s][j];
+                                        E0 = __fmaf_rn(T, __fmul_rn(alpha, ex.x), E0);
+                                        E1 = __fmaf_rn(T, __fmul_rn(alpha, ex.y), E1);
+                                        E2 = __fmaf_rn(T, __fmul_rn(alpha, ex.z), E2);
+                                    }
                                     if (T > 0.5f && test_T < 0.5f)
                                         D = __uint_as_float(__ldg(depth_key + __float_as_uint(col.w)));
                                     T = test_T;
@@ -143,6 +156,11 @@ blend_forward_kernel(const uint2* __restrict__ ranges, const float4* __restrict_
         out_color[pix] = __fmaf_rn(__ldg(bg), T, C0);
         out_color[hw + pix] = __fmaf_rn(__ldg(bg + 1), T, C1);
         out_color[2 * hw + pix] = __fmaf_rn(__ldg(bg + 2), T, C2);
+        if (NCH == 6) {
+            out_color2[pix] = __fmaf_rn(__ldg(bg), T, E0);
+            out_color2[hw + pix] = __fmaf_rn(__ldg(bg + 1), T, E1);
+            out_color2[2 * hw + pix] = __fmaf_rn(__ldg(bg + 2), T, E2);
+        }
         out_depth[pix] = D;
     }
 }
@@ -150,20 +168,22 @@ blend_forward_kernel(const uint2* __restrict__ ranges, const float4* __restrict_
 }  // namespace
 
 int launch_blend_forward(const sb_settings& s, int R, const GeometryWs& g, const BinningWs& b,
-                         const ImageWs& img, float* out_color, float* out_depth, cudaStream_t st) {
+                         const ImageWs& img, float* out_color, float* out_color2, float* out_depth,
+                         cudaStream_t st) {
     (void)R;
     const int W = s.image_width, H = s.image_height;
     const uint32_t gx = (W + kTile - 1) / kTile, gy = (H + kTile - 1) / kTile;
-    static const int variant = [] { const char* e = getenv("SB_FWD_VARIANT"); return e ? atoi(e) : 0; }();
     ScopedStage _p(kStBlendFwd, st);
-    if (variant == 1)
-        blend_forward_kernel<7><<<gx * gy, kBlendThreads, 0, st>>>(img.ranges, b.recA, b.recB, b.recC, g.depth_key,
-                                                                   W, H, gx, s.bg, out_color, out_depth,
-                                                                   img.final_T, img.n_contrib);
+    if (out_color2 != nullptr)
+        blend_forward_kernel<6, 4><<<gx * gy, kBlendThreads, 0, st>>>(img.ranges, b.recA, b.recB, b.recC, b.recD,
+                                                                      g.depth_key, W, H, gx, s.bg, out_color,
+                                                                      out_color2, out_depth, img.final_T,
+                                                                      img.n_contrib);
     else
-        blend_forward_kernel<5><<<gx * gy, kBlendThreads, 0, st>>>(img.ranges, b.recA, b.recB, b.recC, g.depth_key,
-                                                                   W, H, gx, s.bg, out_color, out_depth,
-                                                                   img.final_T, img.n_contrib);
+        blend_forward_kernel<3, 5><<<gx * gy, kBlendThreads, 0, st>>>(img.ranges, b.recA, b.recB, b.recC, nullptr,
+                                                                      g.depth_key, W, H, gx, s.bg, out_color,
+                                                                      nullptr, out_depth, img.final_T,
+                                                                      img.n_contrib);
     SB_LAUNCH_CHECK("blend_forward_kernel");
     return SB_OK;
 }

@@ -79,11 +79,12 @@ struct BinningWs {
     float4*   recA;          // [R]
     float4*   recB;          // [R]
     float4*   recC;          // [R]
+    float4*   recD;          // [R] second colour set {e0, e1, e2, -} (fused two-set render only)
     void*     cub_temp;
     size_t    cub_temp_bytes;
 };
 size_t binning_cub_temp_bytes(int R, bool keys16);
-BinningWs carve_binning(void* ws, int R, int tiles, size_t* total);
+BinningWs carve_binning(void* ws, int R, int tiles, int color_sets, size_t* total);
 
 struct ImageWs {
     uint2*    ranges;     // [tiles] [start,end) into the sorted instance list
@@ -95,6 +96,8 @@ ImageWs carve_image(void* ws, int W, int H, size_t* total);
 // Accumulator written by the backward blend with vector reductions, one 48-B row per Gaussian:
 // {dmean2D.x, dmean2D.y, dconic.xx, dconic.xy, dconic.yy, dopacity, dcolor.r, .g, .b, pad x3}
 constexpr int kAccumStride = 12;
+// fused two-set render: 64-B rows {.. 9 as above .., dcolor2.rgb, dmean2D.xy from the FIRST colour set only, pad x2}
+constexpr int kAccumStride2 = 16;
 
 // ---- reference tile-id bit width (getHigherMsb, X/cuda_rasterizer/rasterizer_impl.cu:35-50) ----
 inline uint32_t higher_msb(uint32_t n) {
@@ -109,16 +112,19 @@ int launch_project(const sb_settings& s, int P, const float* means3D, const floa
                    const float* scales, const float* rotations, const float* cov3D_precomp,
                    int32_t* radii, const GeometryWs& g, cudaStream_t st);
 int launch_depth_order(int P, const GeometryWs& g, cudaStream_t st);
-int launch_binning(const sb_settings& s, int P, int R, const float* colors, const GeometryWs& g,
-                   const BinningWs& b, const ImageWs& img, cudaStream_t st);
+// colors2 / out_color2 / dL2 / dL_dcolors2 == nullptr selects the plain 3-channel path
+int launch_binning(const sb_settings& s, int P, int R, const float* colors, const float* colors2,
+                   const GeometryWs& g, const BinningWs& b, const ImageWs& img, cudaStream_t st);
 int launch_blend_forward(const sb_settings& s, int R, const GeometryWs& g, const BinningWs& b,
-                         const ImageWs& img, float* out_color, float* out_depth, cudaStream_t st);
+                         const ImageWs& img, float* out_color, float* out_color2, float* out_depth,
+                         cudaStream_t st);
 int launch_blend_backward(const sb_settings& s, int R, const BinningWs& b, const ImageWs& img,
-                          const float* dL_dout_color, float* accum, cudaStream_t st);
+                          const float* dL_dout_color, const float* dL_dout_color2, float* accum,
+                          cudaStream_t st);
 int launch_geometry_backward(const sb_settings& s, int P, const float* means3D, const float* colors,
                              const float* scales, const float* rotations, const float* cov3D_precomp,
-                             const int32_t* radii, const float* accum,
-                             float* dL_dmeans3D, float* dL_dmeans2D, float* dL_dcolors,
+                             const int32_t* radii, const float* accum, int accum_stride,
+                             float* dL_dmeans3D, float* dL_dmeans2D, float* dL_dcolors, float* dL_dcolors2,
                              float* dL_dopacity, float* dL_dscales, float* dL_drotations,
                              float* dL_dcov3D, cudaStream_t st);
 int launch_mark_visible(int P, const float* means3D, const float* viewmatrix, uint8_t* present,

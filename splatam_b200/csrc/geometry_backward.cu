@@ -17,9 +17,10 @@ geometry_backward_kernel(int P, const float* __restrict__ means3D, const float* 
                          const float* __restrict__ cov3D_precomp, const int32_t* __restrict__ radii,
                          const float* __restrict__ view, const float* __restrict__ proj,
                          float h_x, float h_y, float tan_fovx, float tan_fovy, float mod,
-                         const float* __restrict__ accum,
+                         const float* __restrict__ accum, int accum_stride,
                          float* __restrict__ dL_dmeans3D, float* __restrict__ dL_dmeans2D,
-                         float* __restrict__ dL_dcolors, float* __restrict__ dL_dopacity,
+                         float* __restrict__ dL_dcolors, float* __restrict__ dL_dcolors2,
+                         float* __restrict__ dL_dopacity,
                          float* __restrict__ dL_dscales, float* __restrict__ dL_drot,
                          float* __restrict__ dL_dcov3D) {
     (void)colors;
@@ -32,14 +33,21 @@ geometry_backward_kernel(int P, const float* __restrict__ means3D, const float* 
     const size_t i3 = 3 * (size_t)idx, i4 = 4 * (size_t)idx, i6 = 6 * (size_t)idx;
 
     float gm[3] = {0.f, 0.f, 0.f}, gm2[2] = {0.f, 0.f}, gc[3] = {0.f, 0.f, 0.f}, gop = 0.f;
+    float gc2[3] = {0.f, 0.f, 0.f}, gm2_out[2] = {0.f, 0.f};   // second colour set; means2D sink (first set only)
     float gs[3] = {0.f, 0.f, 0.f}, gq[4] = {0.f, 0.f, 0.f, 0.f}, gcov[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 
     if (radii[idx] > 0) {
-        const float4* arow = reinterpret_cast<const float4*>(accum + (size_t)idx * kAccumStride);
+        const float4* arow = reinterpret_cast<const float4*>(accum + (size_t)idx * accum_stride);
         const float4 a0 = __ldg(arow), a1 = __ldg(arow + 1), a2 = __ldg(arow + 2);
         gm2[0] = a0.x; gm2[1] = a0.y;
+        gm2_out[0] = a0.x; gm2_out[1] = a0.y;
         const float dconic_x = a0.z, dconic_y = a0.w, dconic_z = a1.x;
         gop = a1.y; gc[0] = a1.z; gc[1] = a1.w; gc[2] = a2.x;
+        if (accum_stride == kAccumStride2) {
+            const float4 a3 = __ldg(arow + 3);
+            gc2[0] = a2.y; gc2[1] = a2.z; gc2[2] = a2.w;
+            gm2_out[0] = a3.x; gm2_out[1] = a3.y;
+        }
 
         const float mx = __ldg(means3D + i3), my = __ldg(means3D + i3 + 1), mz = __ldg(means3D + i3 + 2);
 
@@ -165,8 +173,9 @@ geometry_backward_kernel(int P, const float* __restrict__ means3D, const float* 
     }
 
     dL_dmeans3D[i3] = gm[0]; dL_dmeans3D[i3 + 1] = gm[1]; dL_dmeans3D[i3 + 2] = gm[2];
-    dL_dmeans2D[i3] = gm2[0]; dL_dmeans2D[i3 + 1] = gm2[1]; dL_dmeans2D[i3 + 2] = 0.f;
+    dL_dmeans2D[i3] = gm2_out[0]; dL_dmeans2D[i3 + 1] = gm2_out[1]; dL_dmeans2D[i3 + 2] = 0.f;
     dL_dcolors[i3] = gc[0]; dL_dcolors[i3 + 1] = gc[1]; dL_dcolors[i3 + 2] = gc[2];
+    if (dL_dcolors2) { dL_dcolors2[i3] = gc2[0]; dL_dcolors2[i3 + 1] = gc2[1]; dL_dcolors2[i3 + 2] = gc2[2]; }
     dL_dopacity[idx] = gop;
     if (dL_dscales) { dL_dscales[i3] = gs[0]; dL_dscales[i3 + 1] = gs[1]; dL_dscales[i3 + 2] = gs[2]; }
     if (dL_drot) { dL_drot[i4] = gq[0]; dL_drot[i4 + 1] = gq[1]; dL_drot[i4 + 2] = gq[2]; dL_drot[i4 + 3] = gq[3]; }
@@ -180,16 +189,16 @@ geometry_backward_kernel(int P, const float* __restrict__ means3D, const float* 
 
 int launch_geometry_backward(const sb_settings& s, int P, const float* means3D, const float* colors,
                              const float* scales, const float* rotations, const float* cov3D_precomp,
-                             const int32_t* radii, const float* accum,
-                             float* dL_dmeans3D, float* dL_dmeans2D, float* dL_dcolors,
+                             const int32_t* radii, const float* accum, int accum_stride,
+                             float* dL_dmeans3D, float* dL_dmeans2D, float* dL_dcolors, float* dL_dcolors2,
                              float* dL_dopacity, float* dL_dscales, float* dL_drotations,
                              float* dL_dcov3D, cudaStream_t st) {
     const float focal_y = s.image_height / (2.0f * s.tanfovy), focal_x = s.image_width / (2.0f * s.tanfovx);
     ScopedStage _p(kStGeomBwd, st);
     geometry_backward_kernel<<<(P + 255) / 256, 256, 0, st>>>(
         P, means3D, colors, scales, rotations, cov3D_precomp, radii, s.viewmatrix, s.projmatrix, focal_x,
-        focal_y, s.tanfovx, s.tanfovy, s.scale_modifier, accum, dL_dmeans3D, dL_dmeans2D, dL_dcolors,
-        dL_dopacity, dL_dscales, dL_drotations, dL_dcov3D);
+        focal_y, s.tanfovx, s.tanfovy, s.scale_modifier, accum, accum_stride, dL_dmeans3D, dL_dmeans2D, dL_dcolors,
+        dL_dcolors2, dL_dopacity, dL_dscales, dL_drotations, dL_dcov3D);
     SB_LAUNCH_CHECK("geometry_backward_kernel");
     return SB_OK;
 }

@@ -135,8 +135,15 @@ def mapping_loss(params, frame, render, loss_weights=(0.5, 1.0), ignore_outlier_
     else:
         tg = transform_to_frame(params, frame["id"], gaussians_grad=True, camera_grad=False)
         rv_rgb, rv_depth = rgb_rendervar(params, tg), depth_sil_rendervar(params, frame["w2c"], tg)
-    im, radius, _ = render(frame["cam"], **rv_rgb)
-    depth_sil, _, _ = render(frame["cam"], **rv_depth)
+    if fused_loss and render is default_render:      # N1: both colour sets in one raster pass
+        from .rasterizer import GaussianRasterizer
+        im, depth_sil, radius, _ = GaussianRasterizer(raster_settings=frame["cam"]).forward_fused(
+            means3D=rv_rgb["means3D"], means2D=rv_rgb["means2D"], opacities=rv_rgb["opacities"],
+            colors_precomp=rv_rgb["colors_precomp"], colors_extra=rv_depth["colors_precomp"],
+            scales=rv_rgb["scales"], rotations=rv_rgb["rotations"])
+    else:
+        im, radius, _ = render(frame["cam"], **rv_rgb)
+        depth_sil, _, _ = render(frame["cam"], **rv_depth)
     depth = depth_sil[0:1]
     uncertainty = (depth_sil[2:3] - depth ** 2).detach()
     mask = (frame["depth"] > 0) & (~torch.isnan(depth)) & (~torch.isnan(uncertainty))

@@ -74,7 +74,8 @@ class _State:
     __slots__ = ("geom", "binning", "image", "num_rendered", "settings")
 
 
-def _forward_impl(means3D, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, raster_settings):
+def _forward_impl(means3D, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, raster_settings,
+                  colors2=None):
     lib = _lib.load()
     if means3D.dim() != 2 or means3D.shape[1] != 3:
         # rasterize_points.cu:56-58
@@ -90,6 +91,8 @@ def _forward_impl(means3D, colors_precomp, opacities, scales, rotations, cov3Ds_
     scales = _f32c(scales, "scales")
     rotations = _f32c(rotations, "rotations")
     cov3Ds_precomp = _f32c(cov3Ds_precomp, "cov3D_precomp")
+    colors2 = _f32c(colors2, "colors_extra")
+    sets = 2 if colors2 is not None else 1
 
     with torch.cuda.device(device):
         pack = _SettingsPack(raster_settings, device)
@@ -110,18 +113,25 @@ def _forward_impl(means3D, colors_precomp, opacities, scales, rotations, cov3Ds_
             _ptr(cov3Ds_precomp), _ptr(radii), state.geom.data_ptr(), state.geom.numel(),
             ctypes.byref(R), st), "sb_forward_geometry")
         state.num_rendered = R.value
-        _lib.check(lib.sb_binning_workspace_bytes(R.value, W, H, ctypes.byref(n)), "sb_binning_workspace_bytes")
+        _lib.check(lib.sb_binning_workspace_bytes_ex(R.value, W, H, sets, ctypes.byref(n)),
+                   "sb_binning_workspace_bytes_ex")
         state.binning = _ws(n.value, device)
-        _lib.check(lib.sb_forward_render(
-            ctypes.byref(pack.c), P, R.value, _ptr(colors_precomp), state.geom.data_ptr(), state.geom.numel(),
-            state.binning.data_ptr(), state.binning.numel(), state.image.data_ptr(), state.image.numel(),
-            color.data_ptr(), depth.data_ptr(), st), "sb_forward_render")
-    return color, radii, depth, state, (means3D, colors_precomp, scales, rotations, cov3Ds_precomp)
+        color2 = torch.empty((3, H, W), dtype=torch.float32, device=device) if sets == 2 else None
+        _lib.check(lib.sb_forward_render_ex(
+            ctypes.byref(pack.c), P, R.value, _ptr(colors_precomp), _ptr(colors2), state.geom.data_ptr(),
+            state.geom.numel(), state.binning.data_ptr(), state.binning.numel(), state.image.data_ptr(),
+            state.image.numel(), color.data_ptr(), _ptr(color2), depth.data_ptr(), st), "sb_forward_render_ex")
+    saved = (means3D, colors_precomp, scales, rotations, cov3Ds_precomp)
+    if sets == 2:
+        return color, color2, radii, depth, state, saved + (colors2,)
+    return color, radii, depth, state, saved
 
 
-def _backward_impl(state, saved, radii, grad_out_color):
+def _backward_impl(state, saved, radii, grad_out_color, grad_out_color2=None):
     lib = _lib.load()
-    means3D, colors_precomp, scales, rotations, cov3Ds_precomp = saved
+    means3D, colors_precomp, scales, rotations, cov3Ds_precomp = saved[:5]
+    colors2 = saved[5] if len(saved) > 5 else None
+    sets = 2 if colors2 is not None else 1
     device = means3D.device
     P = means3D.shape[0]
     pack = state.settings
@@ -133,17 +143,21 @@ def _backward_impl(state, saved, radii, grad_out_color):
         g_scales = e(P, 3) if have_sr else torch.zeros((P, 3), dtype=torch.float32, device=device)
         g_rot = e(P, 4) if have_sr else torch.zeros((P, 4), dtype=torch.float32, device=device)
         g_cov3D = e(P, 6)
+        g_colors2 = e(P, 3) if sets == 2 else None
+        grad_out_color2 = _f32c(grad_out_color2, "grad_out_color2") if sets == 2 else None
         n = ctypes.c_size_t(0)
-        _lib.check(lib.sb_backward_workspace_bytes(P, ctypes.byref(n)), "sb_backward_workspace_bytes")
+        _lib.check(lib.sb_backward_workspace_bytes_ex(P, sets, ctypes.byref(n)), "sb_backward_workspace_bytes_ex")
         bwd_ws = _ws(n.value, device)
-        _lib.check(lib.sb_backward(
+        _lib.check(lib.sb_backward_ex(
             ctypes.byref(pack.c), P, state.num_rendered, _ptr(means3D), _ptr(colors_precomp), _ptr(scales),
             _ptr(rotations), _ptr(cov3Ds_precomp), _ptr(radii),
             state.geom.data_ptr(), state.geom.numel(), state.binning.data_ptr(), state.binning.numel(),
             state.image.data_ptr(), state.image.numel(), bwd_ws.data_ptr(), bwd_ws.numel(),
-            _ptr(grad_out_color), _ptr(g_means3D), _ptr(g_means2D), _ptr(g_colors), _ptr(g_opac),
-            _ptr(g_scales) if have_sr else None, _ptr(g_rot) if have_sr else None, _ptr(g_cov3D),
-            _stream(device)), "sb_backward")
+            _ptr(grad_out_color), _ptr(grad_out_color2), _ptr(g_means3D), _ptr(g_means2D), _ptr(g_colors),
+            _ptr(g_colors2), _ptr(g_opac), _ptr(g_scales) if have_sr else None, _ptr(g_rot) if have_sr else None,
+            _ptr(g_cov3D), _stream(device)), "sb_backward_ex")
+    if sets == 2:
+        return g_means3D, g_means2D, g_colors, g_opac, g_scales, g_rot, g_cov3D, g_colors2
     return g_means3D, g_means2D, g_colors, g_opac, g_scales, g_rot, g_cov3D
 
 
@@ -190,6 +204,36 @@ class _RasterizeGaussians(torch.autograd.Function):
                 g_cov3D if needs_cov else None, None)
 
 
+class _RasterizeGaussiansFused(torch.autograd.Function):
+    """Two colour sets over one geometry in one pass: returns (color, color_extra, radii,
+    depth).  Equivalent to two _RasterizeGaussians calls that share every input except colors_precomp;
+    the means2D gradient carries the first set's share only (SplaTAM's densification statistic)."""
+
+    @staticmethod
+    def forward(ctx, means3D, means2D, colors_precomp, colors_extra, opacities, scales, rotations, raster_settings):
+        if P_is_zero(means3D):
+            raise _lib.SplatamB200Error("fused render needs at least one Gaussian")
+        empty = torch.empty(0)
+        color, color2, radii, depth, state, saved = _forward_impl(
+            means3D, colors_precomp, opacities, scales, rotations, empty, raster_settings, colors2=colors_extra)
+        ctx.state = state
+        ctx.opac_shape = opacities.shape
+        ctx.save_for_backward(radii, *[t if t is not None else torch.empty(0) for t in saved])
+        ctx.mark_non_differentiable(radii, depth)
+        return color, color2, radii, depth
+
+    @staticmethod
+    def backward(ctx, grad_color, grad_color2, _grad_radii, _grad_depth):
+        radii, *saved = ctx.saved_tensors
+        if grad_color is None:
+            grad_color = torch.zeros_like(grad_color2)
+        if grad_color2 is None:
+            grad_color2 = torch.zeros_like(grad_color)
+        g_means3D, g_means2D, g_colors, g_opac, g_scales, g_rot, _g_cov, g_colors2 = _backward_impl(
+            ctx.state, tuple(saved), radii, grad_color, grad_color2)
+        return (g_means3D, g_means2D, g_colors, g_colors2, g_opac.reshape(ctx.opac_shape), g_scales, g_rot, None)
+
+
 def P_is_zero(means3D):
     return means3D.shape[0] == 0
 
@@ -220,6 +264,11 @@ class GaussianRasterizer(nn.Module):
                     _lib.check(lib.sb_mark_visible(P, pos.data_ptr(), view.data_ptr(), proj.data_ptr(),
                                                    present.data_ptr(), _stream(pos.device)), "sb_mark_visible")
         return present
+
+    def forward_fused(self, means3D, means2D, opacities, colors_precomp, colors_extra, scales, rotations):
+        """One pass, two colour sets (e.g. SplaTAM's RGB and [depth, 1, depth^2]); see _RasterizeGaussiansFused."""
+        return _RasterizeGaussiansFused.apply(means3D, means2D, colors_precomp, colors_extra, opacities, scales,
+                                              rotations, self.raster_settings)
 
     def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None,
                 cov3D_precomp=None):

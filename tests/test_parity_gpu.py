@@ -199,3 +199,42 @@ def test_cov3d_precomp_branch_vs_reference(cuda_device):
         rcol, rrad, rgcov, rgmean = run(ref)
         assert np.array_equal(col.view(np.uint32), rcol.view(np.uint32)) and np.array_equal(rad, rrad)
         assert l2_rel(gcov, rgcov) < REL and l2_rel(gmean, rgmean) < REL
+
+
+@pytest.mark.parametrize("make", [scenes.config1, scenes.edge_cases, lambda: scenes.dense_opaque(),
+                                  lambda: scenes.room(seed=9, P=100_000, cam=scenes.TUM_FR1, anisotropic=True)])
+def test_fused_two_set_render_equals_two_passes(make, cuda_device):
+    """N1: the fused RGB + depth/silhouette render against two plain renders over the same geometry."""
+    import splatam_b200 as S
+    dev = cuda_device
+    sc = make()
+    rs = sc.settings(S.GaussianRasterizationSettings, dev)
+    rast = S.GaussianRasterizer(rs)
+    g = torch.Generator().manual_seed(8)
+    extra = torch.rand(sc.P, 3, generator=g).to(dev) * 3.0
+    dL1 = torch.randn(3, sc.h, sc.w, generator=g).to(dev)
+    dL2 = torch.randn(3, sc.h, sc.w, generator=g).to(dev)
+    # two plain passes
+    a = sc.inputs(dev, requires_grad=True)
+    ex_a = extra.clone().requires_grad_(True)
+    m2b = torch.zeros_like(a["means3D"], requires_grad=True)
+    c1, r1, d1 = rast(**a)
+    c2, _, _ = rast(means3D=a["means3D"], means2D=m2b, opacities=a["opacities"], colors_precomp=ex_a,
+                    scales=a["scales"], rotations=a["rotations"])
+    ((c1 * dL1).sum() + (c2 * dL2).sum()).backward()
+    # fused
+    b = sc.inputs(dev, requires_grad=True)
+    ex_b = extra.clone().requires_grad_(True)
+    f1, f2, rf, df = rast.forward_fused(means3D=b["means3D"], means2D=b["means2D"], opacities=b["opacities"],
+                                        colors_precomp=b["colors_precomp"], colors_extra=ex_b, scales=b["scales"],
+                                        rotations=b["rotations"])
+    ((f1 * dL1).sum() + (f2 * dL2).sum()).backward()
+    assert torch.equal(f1, c1) and torch.equal(f2, c2) and torch.equal(rf, r1) and torch.equal(df, d1)
+    for k in ["means3D", "colors_precomp", "opacities", "scales", "rotations"]:
+        ga, gb = a[k].grad.cpu().numpy(), b[k].grad.cpu().numpy()
+        if k == "rotations" and np.abs(ga).max() < 1e-9:
+            continue
+        assert l2_rel(gb, ga) < 2e-5, (k, l2_rel(gb, ga))
+    assert l2_rel(ex_b.grad.cpu().numpy(), ex_a.grad.cpu().numpy()) < 2e-5
+    # means2D sink: first colour set only
+    assert l2_rel(b["means2D"].grad.cpu().numpy(), a["means2D"].grad.cpu().numpy()) < 2e-5
