@@ -163,7 +163,6 @@ SB_API int sb_forward_geometry(const sb_settings* s, int P, const float* means3D
     if (P == 0) return SB_OK;  // rasterize_points.cu:81 -- nothing launched for an empty scene
     if (!means3D || !opacities || !radii || !geom_ws) return SB_ERR_BAD_ARG;
     if (!cov3D_precomp && (!scales || !rotations)) return SB_ERR_BAD_ARG;
-    if (s->sh_degree != 0) return SB_ERR_UNSUPPORTED;
     size_t need = 0;
     GeometryWs g = carve_geometry(geom_ws, P, &need);
     if (geom_ws_bytes < need) return SB_ERR_WORKSPACE;

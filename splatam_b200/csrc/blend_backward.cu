@@ -206,11 +206,11 @@ blend_backward_kernel(const uint2* __restrict__ ranges, const float4* __restrict
     int qn = 0;                                        // queued survivors (warp-uniform)
     // shared-space addresses of this lane's queue column and of the warp's meta rows (explicit st.shared:
     // keeps the generic->shared window arithmetic out of the inner loop)
-    const uint32_t qw_lane = smem_u32(&sm.qw[warp][0][lane]);
-    const uint32_t qc_lane = smem_u32(&sm.qc[warp][0][lane]);
-    const uint32_t qr_lane = smem_u32(&sm.qr[NCH == 6 ? warp : 0][0][lane]);
-    const uint32_t meta_row = smem_u32(&sm.meta[warp][0][0]);
-    uint32_t qoff = 0;                                 // qn * kQStride * 4
+    float* const qw_lane = &sm.qw[warp][0][lane];
+    float* const qc_lane = &sm.qc[warp][0][lane];
+    float* const qr_lane = &sm.qr[NCH == 6 ? warp : 0][0][lane];
+    float4* const meta_row = &sm.meta[warp][0][0];
+    uint32_t qoff = 0;                                 // qn * kQStride
 
     for (int k = 0; k < nb; ++k) {
         const int s = k % kStages;
@@ -265,14 +265,14 @@ blend_backward_kernel(const uint2* __restrict__ ranges, const float4* __restrict
                         }
                         last_alpha = alpha;
                     }
-                    sts_f32(qw_lane + qoff, w);
-                    sts_f32(qc_lane + qoff, ca);
-                    if (NCH == 6) sts_f32(qr_lane + qoff, wr);
+                    qw_lane[qoff] = w;
+                    qc_lane[qoff] = ca;
+                    if (NCH == 6) qr_lane[qoff] = wr;
                     if (lane == 0) {
-                        sts_v4(meta_row + qn * 32, a.x - fx0, a.y - fy0, q.x, q.y);
-                        sts_v4(meta_row + qn * 32 + 16, q.z, q.w, col.w, 0.f);
+                        meta_row[2 * qn] = make_float4(a.x - fx0, a.y - fy0, q.x, q.y);
+                        meta_row[2 * qn + 1] = make_float4(q.z, q.w, col.w, 0.f);
                     }
-                    qoff += kQStride * 4;
+                    qoff += kQStride;
                     if (++qn == kQueue) {
                         flush_queue<NCH, kQueue>(sm, warp, lane, kQueue, ddelx_dx, ddely_dy, accum);
                         qn = 0; qoff = 0;

@@ -163,6 +163,61 @@ def mapping_loss(params, frame, render, loss_weights=(0.5, 1.0), ignore_outlier_
     return loss_weights[0] * l_im + loss_weights[1] * l_depth, radius
 
 
+def tracking_loss(params, frame, render, sil_thres=0.99, loss_weights=(0.5, 1.0), fused=False):
+    """SplaTAM get_loss(tracking=True, use_sil_for_loss=True, use_l1=True): only the camera pose of frame
+    `frame["id"]` gets gradient; L1 sums over pixels with silhouette > sil_thres and valid depth
+    (R/scripts/splatam.py:220-224,254-288; weights R/configs/replica/splatam.py:65-68)."""
+    if fused:
+        rv_rgb, rv_depth = fused_rendervars(params, frame["id"], frame["w2c"], camera_grad=True)
+    else:
+        tg = transform_to_frame(params, frame["id"], gaussians_grad=False, camera_grad=True)
+        rv_rgb, rv_depth = rgb_rendervar(params, tg), depth_sil_rendervar(params, frame["w2c"], tg)
+    if fused and render is default_render:
+        from .rasterizer import GaussianRasterizer
+        im, depth_sil, radius, _ = GaussianRasterizer(raster_settings=frame["cam"]).forward_fused(
+            means3D=rv_rgb["means3D"], means2D=rv_rgb["means2D"], opacities=rv_rgb["opacities"],
+            colors_precomp=rv_rgb["colors_precomp"], colors_extra=rv_depth["colors_precomp"],
+            scales=rv_rgb["scales"], rotations=rv_rgb["rotations"])
+    else:
+        im, radius, _ = render(frame["cam"], **rv_rgb)
+        depth_sil, _, _ = render(frame["cam"], **rv_depth)
+    depth, sil = depth_sil[0:1], depth_sil[1]
+    uncertainty = (depth_sil[2:3] - depth ** 2).detach()
+    mask = (frame["depth"] > 0) & (~torch.isnan(depth)) & (~torch.isnan(uncertainty)) & (sil > sil_thres)
+    mask = mask.detach()
+    l_depth = (torch.abs(frame["depth"] - depth) * mask).sum()
+    l_im = (torch.abs(frame["im"] - im) * mask).sum()          # mask broadcast over the 3 channels
+    return loss_weights[0] * l_im + loss_weights[1] * l_depth, radius
+
+
+def track_frame(params, frame, render=None, num_iters=40, lr_rot=0.0004, lr_trans=0.002, fused=None):
+    """SplaTAM's tracking inner loop for one frame (R/scripts/splatam.py:676-744): Adam on the frame's camera
+    quaternion and translation only, keeping the best-loss pose.  `params` holds detached Gaussian tensors and
+    cam_unnorm_rots [1,4,T] / cam_trans [1,3,T] leaf tensors.  Returns the list of per-iteration losses."""
+    render = default_render if render is None else render
+    if fused is None:
+        fused = params["means3D"].is_cuda and render is default_render
+    rots, trans = params["cam_unnorm_rots"], params["cam_trans"]
+    rots.requires_grad_(True); trans.requires_grad_(True)
+    opt = torch.optim.Adam([{"params": [rots], "lr": lr_rot}, {"params": [trans], "lr": lr_trans}], lr=0.0, eps=1e-15)
+    t = frame["id"]
+    best, best_rot, best_tran, losses = None, None, None, []
+    for _ in range(num_iters):
+        opt.zero_grad(set_to_none=True)
+        loss, _ = tracking_loss(params, frame, render, fused=fused)
+        loss.backward()
+        with torch.no_grad():
+            lv = float(loss)
+            if best is None or lv < best:
+                best, best_rot, best_tran = lv, rots[..., t].detach().clone(), trans[..., t].detach().clone()
+        opt.step()
+        losses.append(lv)
+    with torch.no_grad():
+        rots[..., t] = best_rot
+        trans[..., t] = best_tran
+    return losses
+
+
 class FlatGaussians:
     """The five Gaussian parameter tensors as views into ONE flat fp32 buffer, their gradients as
     views into ONE flat gradient bucket of the same layout -- the packed send buffer of the

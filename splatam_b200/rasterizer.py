@@ -167,10 +167,6 @@ class _RasterizeGaussians(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
                 raster_settings):
-        if sh is not None and sh.numel() != 0:
-            raise _lib.SplatamB200Error(
-                "spherical-harmonics colours are not built yet (SB_ERR_UNSUPPORTED); "
-                "SplaTAM always passes colors_precomp (utils/slam_helpers.py:131-138)")
         if P_is_zero(means3D):
             H, W = int(raster_settings.image_height), int(raster_settings.image_width)
             dev = means3D.device
@@ -180,6 +176,21 @@ class _RasterizeGaussians(torch.autograd.Function):
             # rasterize_points.cu:67-75,81: P == 0 returns the zero-filled images without launching
             return (torch.zeros((3, H, W), device=dev), torch.zeros((0,), dtype=torch.int32, device=dev),
                     torch.zeros((1, H, W), device=dev))
+        use_sh = sh is not None and sh.numel() != 0
+        ctx.sh = None
+        if use_sh:     # SH colours -> rgb, then the colours-precomp path (forward.cu:241-247)
+            sh_c = _f32c(sh, "shs")
+            m_c = _f32c(means3D, "means3D")
+            P, M = sh_c.shape[0], sh_c.shape[1]
+            rgb = torch.empty((P, 3), dtype=torch.float32, device=m_c.device)
+            clamped = torch.empty((P,), dtype=torch.uint8, device=m_c.device)
+            campos = _f32c(raster_settings.campos.to(m_c.device), "campos")
+            with torch.cuda.device(m_c.device):
+                _lib.check(_lib.load().sb_sh_forward(P, int(raster_settings.sh_degree), M, m_c.data_ptr(),
+                                                     campos.data_ptr(), sh_c.data_ptr(), rgb.data_ptr(),
+                                                     clamped.data_ptr(), _stream(m_c.device)), "sb_sh_forward")
+            colors_precomp = rgb
+            ctx.sh = (sh_c, clamped, campos, M, int(raster_settings.sh_degree), sh.shape)
         color, radii, depth, state, saved = _forward_impl(
             means3D, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, raster_settings)
         ctx.empty = False
@@ -199,6 +210,18 @@ class _RasterizeGaussians(torch.autograd.Function):
         g_means3D, g_means2D, g_colors, g_opac, g_scales, g_rot, g_cov3D = _backward_impl(
             ctx.state, saved, radii, grad_out_color)
         needs_cov = saved[4].numel() != 0
+        if ctx.sh is not None:
+            sh_c, clamped, campos, M, deg, sh_shape = ctx.sh
+            means3D = saved[0]
+            g_sh = torch.empty((means3D.shape[0], M, 3), dtype=torch.float32, device=means3D.device)
+            with torch.cuda.device(means3D.device):
+                _lib.check(_lib.load().sb_sh_backward(means3D.shape[0], deg, M, means3D.data_ptr(), campos.data_ptr(),
+                                                      sh_c.data_ptr(), clamped.data_ptr(), g_colors.data_ptr(),
+                                                      g_sh.data_ptr(), g_means3D.data_ptr(), _stream(means3D.device)),
+                           "sb_sh_backward")
+            return (g_means3D, g_means2D, g_sh.reshape(sh_shape), None, g_opac.reshape(ctx.opac_shape),
+                    g_scales if not needs_cov else None, g_rot if not needs_cov else None,
+                    g_cov3D if needs_cov else None, None)
         return (g_means3D, g_means2D, None, g_colors, g_opac.reshape(ctx.opac_shape),
                 g_scales if not needs_cov else None, g_rot if not needs_cov else None,
                 g_cov3D if needs_cov else None, None)

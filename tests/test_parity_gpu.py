@@ -238,3 +238,36 @@ def test_fused_two_set_render_equals_two_passes(make, cuda_device):
     assert l2_rel(ex_b.grad.cpu().numpy(), ex_a.grad.cpu().numpy()) < 2e-5
     # means2D sink: first colour set only
     assert l2_rel(b["means2D"].grad.cpu().numpy(), a["means2D"].grad.cpu().numpy()) < 2e-5
+
+
+@pytest.mark.parametrize("deg", [0, 1, 3])
+def test_sh_colour_branch_vs_reference(deg, cuda_device):
+    """The shs / sh_degree branch of the operator (unused by SplaTAM) against the reference extension."""
+    ref = reference_extension()
+    if ref is None:
+        pytest.skip("baseline/_ref not built")
+    import splatam_b200 as S
+    dev = cuda_device
+    sc = scenes.config1(seed=17, P=3000, w=160, h=96)
+    g = torch.Generator().manual_seed(deg)
+    M = 16
+    shs = (torch.randn(sc.P, M, 3, generator=g) * 0.4).to(dev)
+    dL = torch.randn(3, sc.h, sc.w, generator=g).to(dev)
+
+    def run(mod):
+        rs = sc.settings(mod.GaussianRasterizationSettings, dev)._replace(sh_degree=deg, campos=torch.tensor([0.1, -0.2, 0.05], device=dev))
+        inp = sc.inputs(dev, requires_grad=True)
+        sh = shs.clone().requires_grad_(True)
+        color, radii, depth = mod.GaussianRasterizer(rs)(means3D=inp["means3D"], means2D=inp["means2D"], shs=sh,
+                                                         opacities=inp["opacities"], scales=inp["scales"],
+                                                         rotations=inp["rotations"])
+        color.backward(dL)
+        return (color.detach().cpu().numpy(), radii.cpu().numpy(), sh.grad.cpu().numpy(), inp["means3D"].grad.cpu().numpy(),
+                inp["opacities"].grad.cpu().numpy())
+
+    ours, theirs = run(S), run(ref)
+    assert np.array_equal(ours[1], theirs[1])
+    assert (rel_err(ours[0], theirs[0], 1e-3) > REL).mean() < 1e-4
+    for a, b, name in zip(ours[2:], theirs[2:], ["shs", "means3D", "opacities"]):
+        assert l2_rel(a, b) < REL, (name, l2_rel(a, b))
+    assert not ours[2][:, (deg + 1) ** 2:, :].any(), "coefficients above sh_degree get no gradient"
