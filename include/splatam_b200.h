@@ -219,6 +219,18 @@ SB_API int sb_prepare_backward(int P, int scale_dim, int want_pose, const float*
                                float* g_means3D, float* g_unnorm_rotations, float* g_logit_opacities,
                                float* g_log_scales, float* g_pose16, void* stream);
 
+/* Masked L1 terms of SplaTAM's get_loss (R/scripts/splatam.py:254-288): mask = (gt_depth > 0) & !isnan(depth)
+ * & !isnan(depth_sq - depth^2) [& silhouette > sil_thres when use_sil]; depth_sil is the [3,H,W] depth /
+ * silhouette / depth^2 render.  forward: sums[0] = sum|gt_depth - depth|*mask, sums[1] = sum mask,
+ * sums[2] = sum over channels |gt_im - im|*mask (im may be NULL).  backward: gradients w.r.t. depth_sil (only
+ * channel 0 is non-zero) and im, for loss_depth = sums[0] (/ sums[1] if depth_mean) and loss_im = sums[2]. */
+SB_API int sb_masked_l1_forward(const float* depth_sil, const float* gt_depth, const float* im, const float* gt_im,
+                                int H, int W, float sil_thres, int use_sil, double* sums, void* stream);
+SB_API int sb_masked_l1_backward(const float* depth_sil, const float* gt_depth, const float* im, const float* gt_im,
+                                 int H, int W, float sil_thres, int use_sil, int depth_mean, const double* sums,
+                                 const float* g_depth, const float* g_im, float* grad_depth_sil, float* grad_im,
+                                 void* stream);
+
 /* ---- per-stage device timing (measurement only; bench.py's roofline pass) -------------------
  * Between sb_profile_begin() and sb_profile_end() every stage launch of this process is bracketed
  * by CUDA events on its stream.  sb_profile_end synchronises, writes the summed milliseconds and call

@@ -69,6 +69,8 @@ _SIGNATURES = {
     "sb_prepare_backward": (_i, [_i, _i, _i] + [_vp] * 18 + [_vp]),
     "sb_sh_forward": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sb_sh_backward": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "sb_masked_l1_forward": (_i, [_vp, _vp, _vp, _vp, _i, _i, ctypes.c_float, _i, _vp, _vp]),
+    "sb_masked_l1_backward": (_i, [_vp, _vp, _vp, _vp, _i, _i, ctypes.c_float, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sb_profile_begin": (_i, []),
     "sb_profile_end": (_i, [ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int)]),
     "sb_stage_name": (ctypes.c_char_p, [_i]),

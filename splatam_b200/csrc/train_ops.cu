@@ -159,6 +159,72 @@ ssim_l1_backward_kernel(const float* __restrict__ x, const float* __restrict__ y
     gx[o] = go * (w_l1 * sgn / n - w_ssim * (a + 2.f * xv * b + yv * d) / n);
 }
 
+// ---- fused silhouette/validity-masked L1 losses of get_loss (R/scripts/splatam.py:254-288) ---------------
+// mask = (gt_depth > 0) & !isnan(depth) & !isnan(depth_sq - depth^2) [& (silhouette > sil_thres)]
+// sums[0] = sum |gt_depth - depth| * mask, sums[1] = sum mask, sums[2] = sum_ch |gt_im - im| * mask
+__device__ __forceinline__ bool loss_mask(float gd, float d, float sil, float dsq, float sil_thres, int use_sil) {
+    const float unc = dsq - d * d;
+    bool m = gd > 0.f && !isnan(d) && !isnan(unc);
+    if (use_sil) m = m && (sil > sil_thres);
+    return m;
+}
+
+__global__ void __launch_bounds__(256)
+masked_l1_forward_kernel(const float* __restrict__ depth_sil, const float* __restrict__ gt_depth,
+                         const float* __restrict__ im, const float* __restrict__ gt_im, int HW, float sil_thres,
+                         int use_sil, double* __restrict__ sums) {
+    __shared__ float red[3][8];
+    float sd = 0.f, sm = 0.f, si = 0.f;
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < HW; p += gridDim.x * blockDim.x) {
+        const float d = depth_sil[p], gd = gt_depth[p];
+        if (loss_mask(gd, d, depth_sil[HW + p], depth_sil[2 * HW + p], sil_thres, use_sil)) {
+            sd += fabsf(gd - d); sm += 1.f;
+            if (im) si += fabsf(gt_im[p] - im[p]) + fabsf(gt_im[HW + p] - im[HW + p]) + fabsf(gt_im[2 * HW + p] - im[2 * HW + p]);
+        }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        sd += __shfl_xor_sync(0xffffffffu, sd, off); sm += __shfl_xor_sync(0xffffffffu, sm, off);
+        si += __shfl_xor_sync(0xffffffffu, si, off);
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { red[0][warp] = sd; red[1][warp] = sm; red[2][warp] = si; }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        float v = 0.f;
+        for (int w = 0; w < 8; ++w) v += red[threadIdx.x][w];
+        atomicAdd(&sums[threadIdx.x], (double)v);
+    }
+}
+
+// grad_depth_sil[0] = g_d * sign(d - gt) * mask * (mean ? 1/count : 1); channels 1, 2 get zero (the uncertainty
+// and the silhouette mask are detached in the reference); grad_im[ch] = g_i * sign(im - gt) * mask.
+__global__ void __launch_bounds__(256)
+masked_l1_backward_kernel(const float* __restrict__ depth_sil, const float* __restrict__ gt_depth,
+                          const float* __restrict__ im, const float* __restrict__ gt_im, int HW, float sil_thres,
+                          int use_sil, int depth_mean, const double* __restrict__ sums,
+                          const float* __restrict__ g_depth, const float* __restrict__ g_im,
+                          float* __restrict__ grad_depth_sil, float* __restrict__ grad_im) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= HW) return;
+    const float d = depth_sil[p], gd = gt_depth[p];
+    const bool m = loss_mask(gd, d, depth_sil[HW + p], depth_sil[2 * HW + p], sil_thres, use_sil);
+    float scale = g_depth ? __ldg(g_depth) : 0.f;
+    if (depth_mean) scale = scale / (float)sums[1];
+    const float diff = d - gd;
+    grad_depth_sil[p] = m ? scale * (diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f)) : 0.f;
+    grad_depth_sil[HW + p] = 0.f;
+    grad_depth_sil[2 * HW + p] = 0.f;
+    if (grad_im) {
+        const float gi = g_im ? __ldg(g_im) : 0.f;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float df = im[c * HW + p] - gt_im[c * HW + p];
+            grad_im[c * HW + p] = m ? gi * (df > 0.f ? 1.f : (df < 0.f ? -1.f : 0.f)) : 0.f;
+        }
+    }
+}
+
 bool g_gauss_ready = false;
 
 }  // namespace
@@ -184,6 +250,32 @@ SB_API int sb_adam_step(float* params, const float* grads, float* exp_avg, float
     adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(params, grads, exp_avg, exp_avg_sq, n, segs, beta1, beta2,
                                                               eps, (float)bc1, (float)sqrt(bc2));
     SB_LAUNCH_CHECK("adam_kernel");
+    return SB_OK;
+}
+
+/* sums: 3 device doubles (zeroed here).  im / gt_im may be NULL (mapping: the RGB term uses the SSIM loss). */
+SB_API int sb_masked_l1_forward(const float* depth_sil, const float* gt_depth, const float* im, const float* gt_im,
+                                int H, int W, float sil_thres, int use_sil, double* sums, void* stream) {
+    if (!depth_sil || !gt_depth || !sums || H < 1 || W < 1 || ((im != nullptr) != (gt_im != nullptr))) return SB_ERR_BAD_ARG;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    SB_CUDA_CHECK(cudaMemsetAsync(sums, 0, 3 * sizeof(double), st));
+    const int HW = H * W;
+    const int blocks = (HW + 255) / 256 < 592 ? (HW + 255) / 256 : 592;   // 148 SMs x 4
+    masked_l1_forward_kernel<<<blocks, 256, 0, st>>>(depth_sil, gt_depth, im, gt_im, HW, sil_thres, use_sil, sums);
+    SB_LAUNCH_CHECK("masked_l1_forward_kernel");
+    return SB_OK;
+}
+
+SB_API int sb_masked_l1_backward(const float* depth_sil, const float* gt_depth, const float* im, const float* gt_im,
+                                 int H, int W, float sil_thres, int use_sil, int depth_mean, const double* sums,
+                                 const float* g_depth, const float* g_im, float* grad_depth_sil, float* grad_im,
+                                 void* stream) {
+    if (!depth_sil || !gt_depth || !sums || !grad_depth_sil || H < 1 || W < 1) return SB_ERR_BAD_ARG;
+    if (grad_im && (!im || !gt_im)) return SB_ERR_BAD_ARG;
+    const int HW = H * W;
+    masked_l1_backward_kernel<<<(HW + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        depth_sil, gt_depth, im, gt_im, HW, sil_thres, use_sil, depth_mean, sums, g_depth, g_im, grad_depth_sil, grad_im);
+    SB_LAUNCH_CHECK("masked_l1_backward_kernel");
     return SB_OK;
 }
 

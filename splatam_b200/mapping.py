@@ -84,18 +84,33 @@ def depth_sil_rendervar(params, w2c, tg):
                 means2D=torch.zeros_like(params["means3D"], requires_grad=True) + 0)
 
 
+_POSE_CACHE = {}
+
+
 def fused_rendervars(params, time_idx, w2c0, camera_grad):
     """Both rendervars of one frame from ONE fused kernel (splatam_b200/prepare.py); equals
     transform_to_frame + rgb_rendervar + depth_sil_rendervar above to float rounding."""
     from .prepare import prepare_gaussians
-    rot, tran = params["cam_unnorm_rots"][..., time_idx], params["cam_trans"][..., time_idx]
-    if not camera_grad:
-        rot, tran = rot.detach(), tran.detach()
-    cam_rot = F.normalize(rot)
+    rots_all, trans_all = params["cam_unnorm_rots"], params["cam_trans"]
     dev = params["means3D"].device
-    rel_w2c = torch.eye(4, device=dev, dtype=torch.float32)
-    rel_w2c[:3, :3] = build_rotation(cam_rot)
-    rel_w2c[:3, 3] = tran
+    key = None
+    if not camera_grad:     # poses are constants of the mapping loop: build each frame's matrix once
+        key = (id(rots_all), id(trans_all), rots_all._version, trans_all._version, int(time_idx))
+        hit = _POSE_CACHE.get(key)
+        if hit is not None:
+            rel_w2c, cam_rot = hit
+    if key is None or hit is None:
+        rot, tran = rots_all[..., time_idx], trans_all[..., time_idx]
+        if not camera_grad:
+            rot, tran = rot.detach(), tran.detach()
+        cam_rot = F.normalize(rot)
+        rel_w2c = torch.eye(4, device=dev, dtype=torch.float32)
+        rel_w2c[:3, :3] = build_rotation(cam_rot)
+        rel_w2c[:3, 3] = tran
+        if key is not None:
+            if len(_POSE_CACHE) > 256:
+                _POSE_CACHE.clear()
+            _POSE_CACHE[key] = (rel_w2c, cam_rot)
     means_cam, rots, opac, sc3, dcols = prepare_gaussians(params["means3D"], params["unnorm_rotations"],
                                                           params["logit_opacities"], params["log_scales"], rel_w2c,
                                                           cam_rot, w2c0)
@@ -144,16 +159,17 @@ def mapping_loss(params, frame, render, loss_weights=(0.5, 1.0), ignore_outlier_
     else:
         im, radius, _ = render(frame["cam"], **rv_rgb)
         depth_sil, _, _ = render(frame["cam"], **rv_depth)
-    depth = depth_sil[0:1]
-    uncertainty = (depth_sil[2:3] - depth ** 2).detach()
-    mask = (frame["depth"] > 0) & (~torch.isnan(depth)) & (~torch.isnan(uncertainty))
-    if ignore_outlier_depth_loss:
-        err = torch.abs(frame["depth"] - depth) * (frame["depth"] > 0)
-        mask = mask & (err < 10 * err.median())
-    mask = mask.detach()
-    if fused_loss:      # same value as [mask].mean() without the nonzero/index/sort kernels of boolean indexing
-        l_depth = (torch.abs(frame["depth"] - depth) * mask).sum() / mask.sum()
+    if fused_loss and not ignore_outlier_depth_loss:
+        from .train_ops import masked_l1        # validity-masked mean |gt - depth| in one kernel (+ one backward)
+        l_depth, _ = masked_l1(depth_sil, frame["depth"], depth_mean=True)
     else:
+        depth = depth_sil[0:1]
+        uncertainty = (depth_sil[2:3] - depth ** 2).detach()
+        mask = (frame["depth"] > 0) & (~torch.isnan(depth)) & (~torch.isnan(uncertainty))
+        if ignore_outlier_depth_loss:
+            err = torch.abs(frame["depth"] - depth) * (frame["depth"] > 0)
+            mask = mask & (err < 10 * err.median())
+        mask = mask.detach()
         l_depth = torch.abs(frame["depth"] - depth)[mask].mean()
     if fused_loss:      # one forward + one backward kernel instead of 5 depthwise convs + autograd (train_ops.cu)
         from .train_ops import image_loss
@@ -181,12 +197,17 @@ def tracking_loss(params, frame, render, sil_thres=0.99, loss_weights=(0.5, 1.0)
     else:
         im, radius, _ = render(frame["cam"], **rv_rgb)
         depth_sil, _, _ = render(frame["cam"], **rv_depth)
-    depth, sil = depth_sil[0:1], depth_sil[1]
-    uncertainty = (depth_sil[2:3] - depth ** 2).detach()
-    mask = (frame["depth"] > 0) & (~torch.isnan(depth)) & (~torch.isnan(uncertainty)) & (sil > sil_thres)
-    mask = mask.detach()
-    l_depth = (torch.abs(frame["depth"] - depth) * mask).sum()
-    l_im = (torch.abs(frame["im"] - im) * mask).sum()          # mask broadcast over the 3 channels
+    if fused:
+        from .train_ops import masked_l1
+        l_depth, l_im = masked_l1(depth_sil, frame["depth"], im, frame["im"], sil_thres=sil_thres, use_sil=True,
+                                  depth_mean=False)
+    else:
+        depth, sil = depth_sil[0:1], depth_sil[1]
+        uncertainty = (depth_sil[2:3] - depth ** 2).detach()
+        mask = (frame["depth"] > 0) & (~torch.isnan(depth)) & (~torch.isnan(uncertainty)) & (sil > sil_thres)
+        mask = mask.detach()
+        l_depth = (torch.abs(frame["depth"] - depth) * mask).sum()
+        l_im = (torch.abs(frame["im"] - im) * mask).sum()          # mask broadcast over the 3 channels
     return loss_weights[0] * l_im + loss_weights[1] * l_depth, radius
 
 

@@ -76,3 +76,52 @@ def image_loss(im, gt, w_l1=0.8, w_ssim=0.2):
     if not im.is_cuda:
         raise _lib.SplatamB200Error("image_loss needs CUDA tensors (there is no CPU fallback)")
     return _ImageLoss.apply(im, gt, w_l1, w_ssim)
+
+
+class _MaskedL1(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, depth_sil, gt_depth, im, gt_im, sil_thres, use_sil, depth_mean):
+        lib = _lib.load()
+        dev = depth_sil.device
+        depth_sil, gt_depth = depth_sil.contiguous().float(), gt_depth.contiguous().float()
+        _, H, W = depth_sil.shape
+        have_im = im is not None
+        if have_im:
+            im, gt_im = im.contiguous().float(), gt_im.contiguous().float()
+        sums = torch.empty(3, dtype=torch.float64, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.sb_masked_l1_forward(depth_sil.data_ptr(), gt_depth.data_ptr(),
+                                                im.data_ptr() if have_im else None, gt_im.data_ptr() if have_im else None,
+                                                H, W, float(sil_thres), int(use_sil), sums.data_ptr(), _stream(dev)),
+                       "sb_masked_l1_forward")
+        ctx.save_for_backward(depth_sil, gt_depth, sums, *([im, gt_im] if have_im else []))
+        ctx.cfg = (float(sil_thres), int(use_sil), int(depth_mean), have_im)
+        l_depth = (sums[0] / sums[1] if depth_mean else sums[0]).float()
+        return l_depth, sums[2].float()
+
+    @staticmethod
+    def backward(ctx, g_depth, g_im):
+        lib = _lib.load()
+        sil_thres, use_sil, depth_mean, have_im = ctx.cfg
+        depth_sil, gt_depth, sums, *rest = ctx.saved_tensors
+        dev = depth_sil.device
+        _, H, W = depth_sil.shape
+        grad_ds = torch.empty_like(depth_sil)
+        grad_im = torch.empty_like(rest[0]) if have_im else None
+        gd = g_depth.contiguous().float().reshape(1)
+        gi = g_im.contiguous().float().reshape(1) if have_im else None
+        with torch.cuda.device(dev):
+            _lib.check(lib.sb_masked_l1_backward(
+                depth_sil.data_ptr(), gt_depth.data_ptr(), rest[0].data_ptr() if have_im else None,
+                rest[1].data_ptr() if have_im else None, H, W, sil_thres, use_sil, depth_mean, sums.data_ptr(),
+                gd.data_ptr(), gi.data_ptr() if have_im else None, grad_ds.data_ptr(),
+                grad_im.data_ptr() if have_im else None, _stream(dev)), "sb_masked_l1_backward")
+        return grad_ds, None, grad_im, None, None, None, None
+
+
+def masked_l1(depth_sil, gt_depth, im=None, gt_im=None, sil_thres=0.99, use_sil=False, depth_mean=True):
+    """(loss_depth, loss_im) of SplaTAM's get_loss: validity (and optionally silhouette) masked L1 over the depth
+    channel of the [3,H,W] depth/silhouette/depth^2 render and, if `im` is given, over the RGB image (sum)."""
+    if not depth_sil.is_cuda:
+        raise _lib.SplatamB200Error("masked_l1 needs CUDA tensors (there is no CPU fallback)")
+    return _MaskedL1.apply(depth_sil, gt_depth, im, gt_im, sil_thres, use_sil, depth_mean)

@@ -94,3 +94,40 @@ def test_prepare_gaussians_matches_torch_glue(aniso, camgrad, cuda_device):
         assert a is not None and b is not None, k
         err = (a - b).norm() / b.norm().clamp_min(1e-20)
         assert err < 1e-4, (k, float(err))
+
+
+@pytest.mark.parametrize("use_sil,depth_mean,with_im", [(False, True, False), (True, False, True)])
+def test_masked_l1_matches_torch(use_sil, depth_mean, with_im, cuda_device):
+    from splatam_b200.train_ops import masked_l1
+    dev = cuda_device
+    g = torch.Generator().manual_seed(3)
+    H, W = 67, 131
+    ds = torch.rand(3, H, W, generator=g)
+    ds[1] = 0.9 + 0.2 * torch.rand(H, W, generator=g)         # silhouette around the 0.99 threshold
+    ds[0, 5, 7] = float("nan")
+    gt_d = 2.0 * torch.rand(1, H, W, generator=g)
+    gt_d[0, :3] = 0.0                                         # invalid depth rows
+    im, gt_im = torch.rand(3, H, W, generator=g), torch.rand(3, H, W, generator=g)
+    ds, gt_d, im, gt_im = [t.to(dev) for t in (ds, gt_d, im, gt_im)]
+
+    a_ds, a_im = ds.clone().requires_grad_(True), im.clone().requires_grad_(True)
+    ld, li = masked_l1(a_ds, gt_d, a_im if with_im else None, gt_im if with_im else None, sil_thres=0.99,
+                       use_sil=use_sil, depth_mean=depth_mean)
+    (2.0 * ld + (0.5 * li if with_im else 0.0)).backward()
+
+    b_ds, b_im = ds.clone().requires_grad_(True), im.clone().requires_grad_(True)
+    depth = b_ds[0:1]
+    unc = (b_ds[2:3] - depth ** 2).detach()
+    mask = (gt_d > 0) & (~torch.isnan(depth)) & (~torch.isnan(unc))
+    if use_sil:
+        mask = mask & (b_ds[1] > 0.99)
+    mask = mask.detach()
+    rd = torch.abs(gt_d - depth)[mask].mean() if depth_mean else torch.abs(gt_d - depth)[mask].sum()
+    ri = torch.abs(gt_im - b_im)[torch.tile(mask, (3, 1, 1))].sum()
+    (2.0 * rd + (0.5 * ri if with_im else 0.0)).backward()
+    assert abs(float(ld.detach()) - float(rd.detach())) < 1e-5 * max(1.0, abs(float(rd.detach())))
+    ga, gb = torch.nan_to_num(a_ds.grad), torch.nan_to_num(b_ds.grad)
+    assert torch.allclose(ga, gb, rtol=1e-5, atol=1e-7)
+    if with_im:
+        assert abs(float(li.detach()) - float(ri.detach())) < 1e-5 * float(ri.detach())
+        assert torch.allclose(a_im.grad, b_im.grad, rtol=1e-5, atol=1e-7)
