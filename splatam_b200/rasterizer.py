@@ -60,6 +60,59 @@ class _SettingsPack:
             int(rs.sh_degree), _ptr(self.campos), int(bool(rs.prefiltered)))
 
 
+_PACK_CACHE = {}
+
+
+def _settings_pack(rs, device):
+    """sb_settings for a GaussianRasterizationSettings tuple, cached: SplaTAM builds the camera once per
+    resolution (R/utils/recon_helpers.py:4-27) and passes the same tuple to every call.  The cache entry
+    keeps the tuple alive (so ids stay unique) and is invalidated if a tensor is modified in place."""
+    key = (id(rs), str(device))
+    ver = (rs.bg._version, rs.viewmatrix._version, rs.projmatrix._version)
+    hit = _PACK_CACHE.get(key)
+    if hit is not None and hit[0] is rs and hit[1] == ver:
+        return hit[2]
+    if len(_PACK_CACHE) > 64:
+        _PACK_CACHE.clear()
+    pack = _SettingsPack(rs, device)
+    _PACK_CACHE[key] = (rs, ver, pack)
+    return pack
+
+
+_SIZE_CACHE = {}
+
+
+def _sizes(lib, P, W, H, sets):
+    key = (P, W, H, sets)
+    hit = _SIZE_CACHE.get(key)
+    if hit is None:
+        n = ctypes.c_size_t(0)
+        _lib.check(lib.sb_geometry_workspace_bytes(P, ctypes.byref(n)), "sb_geometry_workspace_bytes")
+        geom = n.value
+        _lib.check(lib.sb_image_workspace_bytes(W, H, ctypes.byref(n)), "sb_image_workspace_bytes")
+        img = n.value
+        _lib.check(lib.sb_backward_workspace_bytes_ex(P, sets, ctypes.byref(n)), "sb_backward_workspace_bytes_ex")
+        if len(_SIZE_CACHE) > 256:
+            _SIZE_CACHE.clear()
+        hit = _SIZE_CACHE[key] = (geom, img, n.value)
+    return hit
+
+
+class _on_device:
+    """torch.cuda.device(dev) only when dev is not already current (the context manager costs ~10 us)."""
+
+    def __init__(self, device):
+        self.ctx = None if torch.cuda.current_device() == device.index else torch.cuda.device(device)
+
+    def __enter__(self):
+        if self.ctx is not None:
+            self.ctx.__enter__()
+
+    def __exit__(self, *a):
+        if self.ctx is not None:
+            self.ctx.__exit__(*a)
+
+
 def _ws(nbytes, device):
     return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
 
@@ -94,8 +147,8 @@ def _forward_impl(means3D, colors_precomp, opacities, scales, rotations, cov3Ds_
     colors2 = _f32c(colors2, "colors_extra")
     sets = 2 if colors2 is not None else 1
 
-    with torch.cuda.device(device):
-        pack = _SettingsPack(raster_settings, device)
+    with _on_device(device):
+        pack = _settings_pack(raster_settings, device)
         st = _stream(device)
         color = torch.empty((3, H, W), dtype=torch.float32, device=device)
         depth = torch.empty((1, H, W), dtype=torch.float32, device=device)
@@ -103,10 +156,9 @@ def _forward_impl(means3D, colors_precomp, opacities, scales, rotations, cov3Ds_
         state = _State()
         state.settings = pack
         n = ctypes.c_size_t(0)
-        _lib.check(lib.sb_geometry_workspace_bytes(P, ctypes.byref(n)), "sb_geometry_workspace_bytes")
-        state.geom = _ws(n.value, device)
-        _lib.check(lib.sb_image_workspace_bytes(W, H, ctypes.byref(n)), "sb_image_workspace_bytes")
-        state.image = _ws(n.value, device)
+        geom_bytes, img_bytes, _ = _sizes(lib, P, W, H, sets)
+        state.geom = _ws(geom_bytes, device)
+        state.image = _ws(img_bytes, device)
         R = ctypes.c_int(0)
         _lib.check(lib.sb_forward_geometry(
             ctypes.byref(pack.c), P, _ptr(means3D), _ptr(opacities), _ptr(scales), _ptr(rotations),
@@ -136,7 +188,7 @@ def _backward_impl(state, saved, radii, grad_out_color, grad_out_color2=None):
     P = means3D.shape[0]
     pack = state.settings
     grad_out_color = _f32c(grad_out_color, "grad_out_color")
-    with torch.cuda.device(device):
+    with _on_device(device):
         e = lambda *shape: torch.empty(shape, dtype=torch.float32, device=device)
         g_means3D, g_means2D, g_colors, g_opac = e(P, 3), e(P, 3), e(P, 3), e(P, 1)
         have_sr = scales is not None and scales.numel() != 0
@@ -145,9 +197,8 @@ def _backward_impl(state, saved, radii, grad_out_color, grad_out_color2=None):
         g_cov3D = e(P, 6)
         g_colors2 = e(P, 3) if sets == 2 else None
         grad_out_color2 = _f32c(grad_out_color2, "grad_out_color2") if sets == 2 else None
-        n = ctypes.c_size_t(0)
-        _lib.check(lib.sb_backward_workspace_bytes_ex(P, sets, ctypes.byref(n)), "sb_backward_workspace_bytes_ex")
-        bwd_ws = _ws(n.value, device)
+        W_, H_ = int(pack.c.image_width), int(pack.c.image_height)
+        bwd_ws = _ws(_sizes(lib, P, W_, H_, sets)[2], device)
         _lib.check(lib.sb_backward_ex(
             ctypes.byref(pack.c), P, state.num_rendered, _ptr(means3D), _ptr(colors_precomp), _ptr(scales),
             _ptr(rotations), _ptr(cov3Ds_precomp), _ptr(radii),
