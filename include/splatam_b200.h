@@ -131,6 +131,18 @@ SB_API int sb_backward(const sb_settings* s, int P, int num_rendered,
                 float* dL_dcov3D,
                 void* stream);
 
+/* ---- forward in one call ---------------------------------------------------------------------------------
+ * sb_forward_geometry + sb_forward_render_ex back to back WITHOUT returning to the caller between them, so
+ * the GPU is idle only for the num_rendered read-back itself.  The caller passes a binning workspace sized
+ * from a guess (e.g. the previous call's num_rendered plus slack); if it is too small the call returns
+ * SB_ERR_WORKSPACE with *num_rendered set and stage 1 complete -- the caller then allocates
+ * sb_binning_workspace_bytes_ex(*num_rendered, ...) and finishes with sb_forward_render_ex. */
+SB_API int sb_forward(const sb_settings* s, int P, const float* means3D, const float* opacities, const float* scales,
+               const float* rotations, const float* cov3D_precomp, const float* colors, const float* colors2,
+               int32_t* radii, void* geom_ws, size_t geom_ws_bytes, void* binning_ws, size_t binning_ws_bytes,
+               void* image_ws, size_t image_ws_bytes, float* out_color, float* out_color2, float* out_depth,
+               int* num_rendered, void* stream);
+
 /* ---- fused two-colour-set render ---------------------------------------
  * SplaTAM renders the SAME geometry twice per iteration with different colours_precomp: RGB and
  * [depth, 1, depth^2] (R/scripts/splatam.py:249,253).  The _ex entry points blend both sets in one pass:

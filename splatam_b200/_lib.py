@@ -46,6 +46,8 @@ _SIGNATURES = {
     "sb_backward_workspace_bytes": (_i, [_i, ctypes.POINTER(_sz)]),
     "sb_forward_geometry": (_i, [ctypes.POINTER(SbSettings), _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz,
                                  ctypes.POINTER(_i), _vp]),
+    "sb_forward": (_i, [ctypes.POINTER(SbSettings), _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _sz,
+                        _vp, _sz, _vp, _vp, _vp, ctypes.POINTER(_i), _vp]),
     "sb_forward_render": (_i, [ctypes.POINTER(SbSettings), _i, _i, _vp, _vp, _sz, _vp, _sz, _vp, _sz,
                                _vp, _vp, _vp]),
     "sb_binning_workspace_bytes_ex": (_i, [_i, _i, _i, _i, ctypes.POINTER(_sz)]),

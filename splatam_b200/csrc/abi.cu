@@ -179,6 +179,22 @@ SB_API int sb_forward_geometry(const sb_settings* s, int P, const float* means3D
     return SB_OK;
 }
 
+SB_API int sb_forward(const sb_settings* s, int P, const float* means3D, const float* opacities, const float* scales,
+               const float* rotations, const float* cov3D_precomp, const float* colors, const float* colors2,
+               int32_t* radii, void* geom_ws, size_t geom_ws_bytes, void* binning_ws, size_t binning_ws_bytes,
+               void* image_ws, size_t image_ws_bytes, float* out_color, float* out_color2, float* out_depth,
+               int* num_rendered, void* stream) {
+    int rc = sb_forward_geometry(s, P, means3D, opacities, scales, rotations, cov3D_precomp, radii, geom_ws,
+                                 geom_ws_bytes, num_rendered, stream);
+    if (rc != SB_OK) return rc;
+    size_t need = 0;
+    rc = sb_binning_workspace_bytes_ex(*num_rendered, s->image_width, s->image_height, colors2 ? 2 : 1, &need);
+    if (rc != SB_OK) return rc;
+    if (*num_rendered > 0 && (binning_ws == nullptr || binning_ws_bytes < need)) return SB_ERR_WORKSPACE;
+    return sb_forward_render_ex(s, P, *num_rendered, colors, colors2, geom_ws, geom_ws_bytes, binning_ws,
+                                binning_ws_bytes, image_ws, image_ws_bytes, out_color, out_color2, out_depth, stream);
+}
+
 SB_API int sb_forward_render(const sb_settings* s, int P, int num_rendered, const float* colors,
                       const void* geom_ws, size_t geom_ws_bytes, void* binning_ws, size_t binning_ws_bytes,
                       void* image_ws, size_t image_ws_bytes, float* out_color, float* out_depth, void* stream) {

@@ -80,6 +80,7 @@ def _settings_pack(rs, device):
 
 
 _SIZE_CACHE = {}
+_R_HINT = {}
 
 
 def _sizes(lib, P, W, H, sets):
@@ -160,19 +161,38 @@ def _forward_impl(means3D, colors_precomp, opacities, scales, rotations, cov3Ds_
         state.geom = _ws(geom_bytes, device)
         state.image = _ws(img_bytes, device)
         R = ctypes.c_int(0)
-        _lib.check(lib.sb_forward_geometry(
-            ctypes.byref(pack.c), P, _ptr(means3D), _ptr(opacities), _ptr(scales), _ptr(rotations),
-            _ptr(cov3Ds_precomp), _ptr(radii), state.geom.data_ptr(), state.geom.numel(),
-            ctypes.byref(R), st), "sb_forward_geometry")
-        state.num_rendered = R.value
-        _lib.check(lib.sb_binning_workspace_bytes_ex(R.value, W, H, sets, ctypes.byref(n)),
-                   "sb_binning_workspace_bytes_ex")
-        state.binning = _ws(n.value, device)
         color2 = torch.empty((3, H, W), dtype=torch.float32, device=device) if sets == 2 else None
-        _lib.check(lib.sb_forward_render_ex(
-            ctypes.byref(pack.c), P, R.value, _ptr(colors_precomp), _ptr(colors2), state.geom.data_ptr(),
-            state.geom.numel(), state.binning.data_ptr(), state.binning.numel(), state.image.data_ptr(),
-            state.image.numel(), color.data_ptr(), _ptr(color2), depth.data_ptr(), st), "sb_forward_render_ex")
+        # binning workspace sized from the last num_rendered seen for this problem shape (+12 % slack): the
+        # whole forward is then ONE library call and the GPU only waits for the num_rendered read-back itself
+        hint_key = (P, W, H, sets, device.index)
+        hint = _R_HINT.get(hint_key, 0)
+        if hint > 0:
+            _lib.check(lib.sb_binning_workspace_bytes_ex(int(hint * 1.125) + 4096, W, H, sets, ctypes.byref(n)),
+                       "sb_binning_workspace_bytes_ex")
+            state.binning = _ws(n.value, device)
+            bin_ptr, bin_bytes = state.binning.data_ptr(), state.binning.numel()
+        else:
+            state.binning, bin_ptr, bin_bytes = None, None, 0
+        rc = lib.sb_forward(ctypes.byref(pack.c), P, _ptr(means3D), _ptr(opacities), _ptr(scales), _ptr(rotations),
+                            _ptr(cov3Ds_precomp), _ptr(colors_precomp), _ptr(colors2), _ptr(radii),
+                            state.geom.data_ptr(), state.geom.numel(), bin_ptr, bin_bytes, state.image.data_ptr(),
+                            state.image.numel(), color.data_ptr(), _ptr(color2), depth.data_ptr(), ctypes.byref(R), st)
+        if rc == 2:      # SB_ERR_WORKSPACE: stage 1 is done, the guess was too small -> size exactly and finish
+            _lib.check(lib.sb_binning_workspace_bytes_ex(R.value, W, H, sets, ctypes.byref(n)),
+                       "sb_binning_workspace_bytes_ex")
+            state.binning = _ws(n.value, device)
+            _lib.check(lib.sb_forward_render_ex(
+                ctypes.byref(pack.c), P, R.value, _ptr(colors_precomp), _ptr(colors2), state.geom.data_ptr(),
+                state.geom.numel(), state.binning.data_ptr(), state.binning.numel(), state.image.data_ptr(),
+                state.image.numel(), color.data_ptr(), _ptr(color2), depth.data_ptr(), st), "sb_forward_render_ex")
+        else:
+            _lib.check(rc, "sb_forward")
+        if state.binning is None:
+            state.binning = _ws(16, device)
+        state.num_rendered = R.value
+        _R_HINT[hint_key] = R.value
+        if len(_R_HINT) > 256:
+            _R_HINT.clear()
     saved = (means3D, colors_precomp, scales, rotations, cov3Ds_precomp)
     if sets == 2:
         return color, color2, radii, depth, state, saved + (colors2,)
