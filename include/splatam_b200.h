@@ -143,6 +143,21 @@ SB_API int sb_forward(const sb_settings* s, int P, const float* means3D, const f
                void* image_ws, size_t image_ws_bytes, float* out_color, float* out_color2, float* out_depth,
                int* num_rendered, void* stream);
 
+/* ---- sync-free forward (CUDA-graph capturable) -------------------------------------------------------------
+ * Same work as sb_forward but num_rendered never leaves the device: the caller fixes a CAPACITY (tile
+ * instances) for the binning workspace (sb_binning_workspace_bytes_ex(capacity, ...)); unused slots are padded
+ * with a sentinel tile id and sorted to the end.  No memcpy to the host, no synchronisation, no allocation:
+ * the call (and sb_backward_ex with num_rendered := capacity) can be captured into a CUDA graph.
+ * If the scene needs more than `capacity` instances the overflow flag is set and the images are incomplete;
+ * sb_read_counts (which synchronises) returns the true count and the flag so the caller can grow and redo. */
+SB_API int sb_forward_async(const sb_settings* s, int P, const float* means3D, const float* opacities,
+                     const float* scales, const float* rotations, const float* cov3D_precomp, const float* colors,
+                     const float* colors2, int32_t* radii, void* geom_ws, size_t geom_ws_bytes, void* binning_ws,
+                     size_t binning_ws_bytes, int capacity, void* image_ws, size_t image_ws_bytes, float* out_color,
+                     float* out_color2, float* out_depth, void* stream);
+SB_API int sb_read_counts(const void* geom_ws, size_t geom_ws_bytes, int P, int* num_rendered, int* overflow,
+                          void* stream);
+
 /* ---- fused two-colour-set render ---------------------------------------
  * SplaTAM renders the SAME geometry twice per iteration with different colours_precomp: RGB and
  * [depth, 1, depth^2] (R/scripts/splatam.py:249,253).  The _ex entry points blend both sets in one pass:

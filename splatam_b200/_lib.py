@@ -48,6 +48,9 @@ _SIGNATURES = {
                                  ctypes.POINTER(_i), _vp]),
     "sb_forward": (_i, [ctypes.POINTER(SbSettings), _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _sz,
                         _vp, _sz, _vp, _vp, _vp, ctypes.POINTER(_i), _vp]),
+    "sb_forward_async": (_i, [ctypes.POINTER(SbSettings), _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _sz,
+                              _i, _vp, _sz, _vp, _vp, _vp, _vp]),
+    "sb_read_counts": (_i, [_vp, _sz, _i, ctypes.POINTER(_i), ctypes.POINTER(_i), _vp]),
     "sb_forward_render": (_i, [ctypes.POINTER(SbSettings), _i, _i, _vp, _vp, _sz, _vp, _sz, _vp, _sz,
                                _vp, _vp, _vp]),
     "sb_binning_workspace_bytes_ex": (_i, [_i, _i, _i, _i, ctypes.POINTER(_sz)]),

@@ -51,7 +51,7 @@ BinningWs carve_binning(void* ws, int R, int tiles, int color_sets, size_t* tota
     Carver c(ws);
     BinningWs b;
     const size_t n = (size_t)(R > 0 ? R : 1);
-    const bool keys16 = higher_msb((uint32_t)tiles) <= 16;
+    const bool keys16 = higher_msb((uint32_t)tiles) <= 16 && tiles < 65535;
     b.tile_unsorted = c.take<uint32_t>(keys16 ? (n + 1) / 2 : n);
     b.val_unsorted = c.take<uint32_t>(n);
     b.tile_sorted = c.take<uint32_t>(keys16 ? (n + 1) / 2 : n);
@@ -195,6 +195,48 @@ SB_API int sb_forward(const sb_settings* s, int P, const float* means3D, const f
                                 binning_ws_bytes, image_ws, image_ws_bytes, out_color, out_color2, out_depth, stream);
 }
 
+SB_API int sb_forward_async(const sb_settings* s, int P, const float* means3D, const float* opacities,
+                     const float* scales, const float* rotations, const float* cov3D_precomp, const float* colors,
+                     const float* colors2, int32_t* radii, void* geom_ws, size_t geom_ws_bytes, void* binning_ws,
+                     size_t binning_ws_bytes, int capacity, void* image_ws, size_t image_ws_bytes, float* out_color,
+                     float* out_color2, float* out_depth, void* stream) {
+    if (!settings_ok(s) || P <= 0 || capacity < 1 || !means3D || !opacities || !radii || !geom_ws || !binning_ws ||
+        !image_ws || !colors || !out_color || !out_depth)
+        return SB_ERR_BAD_ARG;
+    if (!cov3D_precomp && (!scales || !rotations)) return SB_ERR_BAD_ARG;
+    if ((colors2 != nullptr) != (out_color2 != nullptr)) return SB_ERR_BAD_ARG;
+    const int sets = colors2 ? 2 : 1;
+    size_t need = 0;
+    GeometryWs g = carve_geometry(geom_ws, P, &need);
+    if (geom_ws_bytes < need) return SB_ERR_WORKSPACE;
+    BinningWs b = carve_binning(binning_ws, capacity, tiles_of(s), sets, &need);
+    if (binning_ws_bytes < need) return SB_ERR_WORKSPACE;
+    ImageWs img = carve_image(image_ws, s->image_width, s->image_height, &need);
+    if (image_ws_bytes < need) return SB_ERR_WORKSPACE;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int rc = launch_project(*s, P, means3D, opacities, scales, rotations, cov3D_precomp, radii, g, st);
+    if (rc != SB_OK) return rc;
+    if ((rc = launch_depth_order(P, g, st)) != SB_OK) return rc;
+    if ((rc = launch_finalize_count(P, g, capacity, st)) != SB_OK) return rc;
+    if ((rc = launch_binning(*s, P, capacity, colors, colors2, g, b, img, g.header, st)) != SB_OK) return rc;
+    return launch_blend_forward(*s, capacity, g, b, img, out_color, out_color2, out_depth, st);
+}
+
+SB_API int sb_read_counts(const void* geom_ws, size_t geom_ws_bytes, int P, int* num_rendered, int* overflow,
+                          void* stream) {
+    if (!geom_ws || P <= 0 || !num_rendered || !overflow) return SB_ERR_BAD_ARG;
+    size_t need = 0;
+    GeometryWs g = carve_geometry(const_cast<void*>(geom_ws), P, &need);
+    if (geom_ws_bytes < need) return SB_ERR_WORKSPACE;
+    int32_t h[4] = {0, 0, 0, 0};
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    SB_CUDA_CHECK(cudaMemcpyAsync(h, g.header, sizeof(h), cudaMemcpyDeviceToHost, st));
+    SB_CUDA_CHECK(cudaStreamSynchronize(st));
+    *num_rendered = h[0];
+    *overflow = h[2];
+    return SB_OK;
+}
+
 SB_API int sb_forward_render(const sb_settings* s, int P, int num_rendered, const float* colors,
                       const void* geom_ws, size_t geom_ws_bytes, void* binning_ws, size_t binning_ws_bytes,
                       void* image_ws, size_t image_ws_bytes, float* out_color, float* out_depth, void* stream) {
@@ -219,7 +261,7 @@ SB_API int sb_forward_render_ex(const sb_settings* s, int P, int num_rendered, c
     ImageWs img = carve_image(image_ws, s->image_width, s->image_height, &need);
     if (image_ws_bytes < need) return SB_ERR_WORKSPACE;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    int rc = launch_binning(*s, P, num_rendered, colors, colors2, g, b, img, st);
+    int rc = launch_binning(*s, P, num_rendered, colors, colors2, g, b, img, nullptr, st);
     if (rc != SB_OK) return rc;
     return launch_blend_forward(*s, num_rendered, g, b, img, out_color, out_color2, out_depth, st);
 }

@@ -113,8 +113,12 @@ int launch_project(const sb_settings& s, int P, const float* means3D, const floa
                    int32_t* radii, const GeometryWs& g, cudaStream_t st);
 int launch_depth_order(int P, const GeometryWs& g, cudaStream_t st);
 // colors2 / out_color2 / dL2 / dL_dcolors2 == nullptr selects the plain 3-channel path
+// count_dev != nullptr selects the sync-free mode: R is then the CAPACITY of the instance arrays and the true
+// instance count is read on the device from *count_dev
 int launch_binning(const sb_settings& s, int P, int R, const float* colors, const float* colors2,
-                   const GeometryWs& g, const BinningWs& b, const ImageWs& img, cudaStream_t st);
+                   const GeometryWs& g, const BinningWs& b, const ImageWs& img, const int32_t* count_dev,
+                   cudaStream_t st);
+int launch_finalize_count(int P, const GeometryWs& g, int capacity, cudaStream_t st);
 int launch_blend_forward(const sb_settings& s, int R, const GeometryWs& g, const BinningWs& b,
                          const ImageWs& img, float* out_color, float* out_color2, float* out_depth,
                          cudaStream_t st);

@@ -244,6 +244,13 @@ mark_visible_kernel(int P, const float* __restrict__ means3D, const float* __res
     present[idx] = (xform_row(vm, 2, px, py, pz) <= 0.2f) ? 0 : 1;  // in_frustum(): `!(z <= 0.2f)`
 }
 
+// header[0] = num_rendered, header[2] = 1 if it exceeds the caller's capacity (sync-free mode)
+__global__ void finalize_count_kernel(const uint32_t* __restrict__ last_offset, int32_t* __restrict__ header, int cap) {
+    const uint32_t R = *last_offset;
+    header[0] = (int32_t)min(R, 0x7fffffffu);
+    header[2] = (R > (uint32_t)cap) ? 1 : 0;
+}
+
 struct TilesInDepthOrder {
     const uint32_t* tiles_touched;
     const uint32_t* sorted_idx;
@@ -297,6 +304,12 @@ int launch_depth_order(int P, const GeometryWs& g, cudaStream_t st) {
     tb = g.cub_temp_bytes;
     ScopedStage _p(kStDepthScan, st);
     SB_CUDA_CHECK(cub::DeviceScan::InclusiveSum(g.cub_temp, tb, it, g.offsets, P, st));
+    return SB_OK;
+}
+
+int launch_finalize_count(int P, const GeometryWs& g, int capacity, cudaStream_t st) {
+    finalize_count_kernel<<<1, 1, 0, st>>>(g.offsets + (P - 1), g.header, capacity);
+    SB_LAUNCH_CHECK("finalize_count_kernel");
     return SB_OK;
 }
 

@@ -81,6 +81,7 @@ def _settings_pack(rs, device):
 
 _SIZE_CACHE = {}
 _R_HINT = {}
+_LAST_ASYNC_STATE = [None]
 
 
 def _sizes(lib, P, W, H, sets):
@@ -125,11 +126,19 @@ def _stream(device):
 class _State:
     """Scratch kept alive between forward and backward (the reference saves its three byte buffers
     on the autograd ctx, __init__.py:82-84)."""
-    __slots__ = ("geom", "binning", "image", "num_rendered", "settings")
+    __slots__ = ("geom", "binning", "image", "num_rendered", "settings", "P")
+
+    def counts(self):
+        """(num_rendered, overflowed) of a sync-free forward; synchronises the current stream."""
+        lib = _lib.load()
+        r, o = ctypes.c_int(0), ctypes.c_int(0)
+        _lib.check(lib.sb_read_counts(self.geom.data_ptr(), self.geom.numel(), self.P, ctypes.byref(r), ctypes.byref(o),
+                                      _stream(self.geom.device)), "sb_read_counts")
+        return r.value, bool(o.value)
 
 
 def _forward_impl(means3D, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, raster_settings,
-                  colors2=None):
+                  colors2=None, capacity=None):
     lib = _lib.load()
     if means3D.dim() != 2 or means3D.shape[1] != 3:
         # rasterize_points.cu:56-58
@@ -156,12 +165,30 @@ def _forward_impl(means3D, colors_precomp, opacities, scales, rotations, cov3Ds_
         radii = torch.empty((P,), dtype=torch.int32, device=device)
         state = _State()
         state.settings = pack
+        state.P = P
         n = ctypes.c_size_t(0)
         geom_bytes, img_bytes, _ = _sizes(lib, P, W, H, sets)
         state.geom = _ws(geom_bytes, device)
         state.image = _ws(img_bytes, device)
         R = ctypes.c_int(0)
         color2 = torch.empty((3, H, W), dtype=torch.float32, device=device) if sets == 2 else None
+        if capacity is not None:
+            # sync-free mode: fixed-capacity binning workspace, num_rendered stays on the device (CUDA-graph safe)
+            capacity = int(capacity)
+            _lib.check(lib.sb_binning_workspace_bytes_ex(capacity, W, H, sets, ctypes.byref(n)),
+                       "sb_binning_workspace_bytes_ex")
+            state.binning = _ws(n.value, device)
+            _lib.check(lib.sb_forward_async(
+                ctypes.byref(pack.c), P, _ptr(means3D), _ptr(opacities), _ptr(scales), _ptr(rotations),
+                _ptr(cov3Ds_precomp), _ptr(colors_precomp), _ptr(colors2), _ptr(radii), state.geom.data_ptr(),
+                state.geom.numel(), state.binning.data_ptr(), state.binning.numel(), capacity, state.image.data_ptr(),
+                state.image.numel(), color.data_ptr(), _ptr(color2), depth.data_ptr(), st), "sb_forward_async")
+            state.num_rendered = capacity
+            _LAST_ASYNC_STATE[0] = state
+            saved = (means3D, colors_precomp, scales, rotations, cov3Ds_precomp)
+            if sets == 2:
+                return color, color2, radii, depth, state, saved + (colors2,)
+            return color, radii, depth, state, saved
         # binning workspace sized from the last num_rendered seen for this problem shape (+12 % slack): the
         # whole forward is then ONE library call and the GPU only waits for the num_rendered read-back itself
         hint_key = (P, W, H, sets, device.index)
@@ -237,7 +264,7 @@ class _RasterizeGaussians(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
-                raster_settings):
+                raster_settings, capacity=None):
         if P_is_zero(means3D):
             H, W = int(raster_settings.image_height), int(raster_settings.image_width)
             dev = means3D.device
@@ -263,7 +290,7 @@ class _RasterizeGaussians(torch.autograd.Function):
             colors_precomp = rgb
             ctx.sh = (sh_c, clamped, campos, M, int(raster_settings.sh_degree), sh.shape)
         color, radii, depth, state, saved = _forward_impl(
-            means3D, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, raster_settings)
+            means3D, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, raster_settings, capacity=capacity)
         ctx.empty = False
         ctx.state = state
         ctx.opac_shape = opacities.shape
@@ -276,7 +303,7 @@ class _RasterizeGaussians(torch.autograd.Function):
         # depth carries no gradient (the reference drops it, __init__.py:88)
         if ctx.empty:
             z = [torch.zeros(s) for s in ctx.shapes]
-            return z[0], z[1], None, z[2], z[3], z[4], z[5], None, None
+            return z[0], z[1], None, z[2], z[3], z[4], z[5], None, None, None
         radii, *saved = ctx.saved_tensors
         g_means3D, g_means2D, g_colors, g_opac, g_scales, g_rot, g_cov3D = _backward_impl(
             ctx.state, saved, radii, grad_out_color)
@@ -292,10 +319,10 @@ class _RasterizeGaussians(torch.autograd.Function):
                            "sb_sh_backward")
             return (g_means3D, g_means2D, g_sh.reshape(sh_shape), None, g_opac.reshape(ctx.opac_shape),
                     g_scales if not needs_cov else None, g_rot if not needs_cov else None,
-                    g_cov3D if needs_cov else None, None)
+                    g_cov3D if needs_cov else None, None, None)
         return (g_means3D, g_means2D, None, g_colors, g_opac.reshape(ctx.opac_shape),
                 g_scales if not needs_cov else None, g_rot if not needs_cov else None,
-                g_cov3D if needs_cov else None, None)
+                g_cov3D if needs_cov else None, None, None)
 
 
 class _RasterizeGaussiansFused(torch.autograd.Function):
@@ -304,12 +331,14 @@ class _RasterizeGaussiansFused(torch.autograd.Function):
     the means2D gradient carries the first set's share only (SplaTAM's densification statistic)."""
 
     @staticmethod
-    def forward(ctx, means3D, means2D, colors_precomp, colors_extra, opacities, scales, rotations, raster_settings):
+    def forward(ctx, means3D, means2D, colors_precomp, colors_extra, opacities, scales, rotations, raster_settings,
+                capacity=None):
         if P_is_zero(means3D):
             raise _lib.SplatamB200Error("fused render needs at least one Gaussian")
         empty = torch.empty(0)
         color, color2, radii, depth, state, saved = _forward_impl(
-            means3D, colors_precomp, opacities, scales, rotations, empty, raster_settings, colors2=colors_extra)
+            means3D, colors_precomp, opacities, scales, rotations, empty, raster_settings, colors2=colors_extra,
+            capacity=capacity)
         ctx.state = state
         ctx.opac_shape = opacities.shape
         ctx.save_for_backward(radii, *[t if t is not None else torch.empty(0) for t in saved])
@@ -325,7 +354,7 @@ class _RasterizeGaussiansFused(torch.autograd.Function):
             grad_color2 = torch.zeros_like(grad_color)
         g_means3D, g_means2D, g_colors, g_opac, g_scales, g_rot, _g_cov, g_colors2 = _backward_impl(
             ctx.state, tuple(saved), radii, grad_color, grad_color2)
-        return (g_means3D, g_means2D, g_colors, g_colors2, g_opac.reshape(ctx.opac_shape), g_scales, g_rot, None)
+        return (g_means3D, g_means2D, g_colors, g_colors2, g_opac.reshape(ctx.opac_shape), g_scales, g_rot, None, None)
 
 
 def P_is_zero(means3D):
@@ -333,15 +362,25 @@ def P_is_zero(means3D):
 
 
 def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
-                        raster_settings):
+                        raster_settings, capacity=None):
     return _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
-                                     cov3Ds_precomp, raster_settings)
+                                     cov3Ds_precomp, raster_settings, capacity)
 
 
 class GaussianRasterizer(nn.Module):
-    def __init__(self, raster_settings):
+    def __init__(self, raster_settings, max_rendered=None):
+        """`max_rendered` (extension): fixed capacity, in tile instances, of the binning workspace.  When given,
+        the forward never synchronises with the host (num_rendered stays on the device) and forward + backward
+        can be captured into a CUDA graph; `last_counts()` reports the true count and whether it overflowed."""
         super().__init__()
         self.raster_settings = raster_settings
+        self.max_rendered = max_rendered
+
+    @staticmethod
+    def last_counts():
+        """(num_rendered, overflowed) of the most recent sync-free forward of this process; synchronises."""
+        st = _LAST_ASYNC_STATE[0]
+        return None if st is None else st.counts()
 
     def markVisible(self, positions):
         """Boolean mask ``view_z > 0.2`` per point (reference __init__.py:152-161)."""
@@ -362,7 +401,7 @@ class GaussianRasterizer(nn.Module):
     def forward_fused(self, means3D, means2D, opacities, colors_precomp, colors_extra, scales, rotations):
         """One pass, two colour sets (e.g. SplaTAM's RGB and [depth, 1, depth^2]); see _RasterizeGaussiansFused."""
         return _RasterizeGaussiansFused.apply(means3D, means2D, colors_precomp, colors_extra, opacities, scales,
-                                              rotations, self.raster_settings)
+                                              rotations, self.raster_settings, self.max_rendered)
 
     def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None,
                 cov3D_precomp=None):
@@ -384,4 +423,4 @@ class GaussianRasterizer(nn.Module):
         if cov3D_precomp is None:
             cov3D_precomp = torch.Tensor([])
         return rasterize_gaussians(means3D, means2D, shs, colors_precomp, opacities, scales, rotations,
-                                   cov3D_precomp, raster_settings)
+                                   cov3D_precomp, raster_settings, self.max_rendered)

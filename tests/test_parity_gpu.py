@@ -271,3 +271,58 @@ def test_sh_colour_branch_vs_reference(deg, cuda_device):
     for a, b, name in zip(ours[2:], theirs[2:], ["shs", "means3D", "opacities"]):
         assert l2_rel(a, b) < REL, (name, l2_rel(a, b))
     assert not ours[2][:, (deg + 1) ** 2:, :].any(), "coefficients above sh_degree get no gradient"
+
+
+def test_sync_free_forward_matches_and_graph_captures(cuda_device):
+    """max_rendered (sync-free, fixed-capacity) mode: identical images, gradients within atomics noise, overflow
+    flag when the capacity is too small, and forward+backward replayable from a CUDA graph."""
+    import splatam_b200 as S
+    dev = cuda_device
+    sc = scenes.config3(P=200_000)
+    rs = sc.settings(S.GaussianRasterizationSettings, dev)
+    dL = torch.randn(3, sc.h, sc.w, generator=torch.Generator().manual_seed(3)).to(dev)
+    a = sc.inputs(dev, requires_grad=True)
+    c0, r0, d0 = S.GaussianRasterizer(rs)(**a)
+    R = c0.grad_fn.state.num_rendered
+    c0.backward(dL)
+    rast = S.GaussianRasterizer(rs, max_rendered=int(R * 1.3))
+    b = sc.inputs(dev, requires_grad=True)
+    c1, r1, d1 = rast(**b)
+    c1.backward(dL)
+    assert rast.last_counts() == (R, False)
+    assert torch.equal(c1, c0) and torch.equal(r1, r0) and torch.equal(d1, d0)
+    for k in ["means3D", "colors_precomp", "opacities", "scales"]:
+        assert l2_rel(b[k].grad.cpu().numpy(), a[k].grad.cpu().numpy()) < 1e-5, k
+    # overflow is reported, not silent
+    small = S.GaussianRasterizer(rs, max_rendered=R // 2)
+    with torch.no_grad():
+        small(**sc.inputs(dev))
+    assert small.last_counts() == (R, True)
+    # CUDA graph: capture forward + backward once, replay with new inputs in the static buffers
+    static = sc.inputs(dev, requires_grad=True)
+    leaves = [static[k] for k in ["means3D", "means2D", "colors_precomp", "opacities", "scales", "rotations"]]
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            for t in leaves:
+                t.grad = None
+            rast(**static)[0].backward(dL)
+    torch.cuda.current_stream().wait_stream(side)
+    for t in leaves:
+        t.grad = None
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        out, _, _ = rast(**static)
+        out.backward(dL)
+    with torch.no_grad():
+        static["colors_precomp"].mul_(0.5)           # change an input in place, replay
+    graph.replay()
+    torch.cuda.synchronize()
+    ref_in = sc.inputs(dev, requires_grad=True)
+    with torch.no_grad():
+        ref_in["colors_precomp"].mul_(0.5)
+    cr, _, _ = S.GaussianRasterizer(rs)(**ref_in)
+    cr.backward(dL)
+    assert torch.equal(out, cr)
+    assert l2_rel(static["means3D"].grad.cpu().numpy(), ref_in["means3D"].grad.cpu().numpy()) < 1e-5
