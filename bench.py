@@ -234,10 +234,14 @@ def mapping_bench(dev, world, dist_on, impl, steps=8, warmup=3, P=1_000_000):
     # kernels on it; ours uses the fused glue + fused two-set render + fused loss + fused Adam
     if impl == "ours":
         mapper = M.ShardedMapper(gauss, rots.to(dev), trans.to(dev), seed=11, fused=True)
+        mapper.enable_graph(frames)       # loss fwd+bwd of a keyframe as one CUDA graph over the sync-free rasterizer
     else:
         render = (lambda settings, **rv: Rast(raster_settings=settings)(**rv))
         mapper = M.ShardedMapper(gauss, rots.to(dev), trans.to(dev), render=render, seed=11, fused=False)
     ms = timed(lambda: mapper.step(frames), steps, warmup, dev, dist_on) / steps
+    if impl == "ours":
+        n_r, overflow = mapper.check_capacity()
+        assert not overflow, "sync-free capacity overflowed: the mapping numbers would be invalid"
     return dict(metric="mapping keyframe-iters/sec", value=world * 1000.0 / ms, unit="keyframe-iters/s",
                 ms_per_step=ms, keyframes_per_step=world, gaussians=P, width=sc.w, height=sc.h,
                 allreduce_bytes=int(mapper.g.flat_grad.numel() * 4) if world > 1 else 0,

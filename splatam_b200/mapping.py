@@ -87,26 +87,53 @@ def depth_sil_rendervar(params, w2c, tg):
 _POSE_CACHE = {}
 
 
-def fused_rendervars(params, time_idx, w2c0, camera_grad):
+def fused_pose_cached(params, time_idx):
+    """Cached (rel_w2c, cam_rot) of a frame whose pose is not being optimised."""
+    rots_all, trans_all = params["cam_unnorm_rots"], params["cam_trans"]
+    key = (id(rots_all), id(trans_all), rots_all._version, trans_all._version, int(time_idx))
+    hit = _POSE_CACHE.get(key)
+    if hit is None:
+        if len(_POSE_CACHE) > 256:
+            _POSE_CACHE.clear()
+        hit = _POSE_CACHE[key] = pose_matrices(params, time_idx)
+    return hit
+
+
+def _last_num_rendered():
+    from . import rasterizer
+    return rasterizer._LAST_SYNC_R[0]
+
+
+def pose_matrices(params, time_idx, camera_grad=False):
+    """(rel_w2c [4,4], normalised camera quaternion [1,4]) of frame `time_idx` (slam_helpers.py:266-275)."""
+    rot, tran = params["cam_unnorm_rots"][..., time_idx], params["cam_trans"][..., time_idx]
+    if not camera_grad:
+        rot, tran = rot.detach(), tran.detach()
+    cam_rot = F.normalize(rot)
+    rel_w2c = torch.eye(4, device=params["means3D"].device, dtype=torch.float32)
+    rel_w2c[:3, :3] = build_rotation(cam_rot)
+    rel_w2c[:3, 3] = tran
+    return rel_w2c, cam_rot
+
+
+def fused_rendervars(params, time_idx, w2c0, camera_grad, pose=None):
     """Both rendervars of one frame from ONE fused kernel (splatam_b200/prepare.py); equals
-    transform_to_frame + rgb_rendervar + depth_sil_rendervar above to float rounding."""
+    transform_to_frame + rgb_rendervar + depth_sil_rendervar above to float rounding.  `pose` = precomputed
+    (rel_w2c, cam_rot) tensors (the CUDA-graph path keeps them in static buffers)."""
     from .prepare import prepare_gaussians
     rots_all, trans_all = params["cam_unnorm_rots"], params["cam_trans"]
     dev = params["means3D"].device
-    key = None
-    if not camera_grad:     # poses are constants of the mapping loop: build each frame's matrix once
+    key = hit = None
+    if pose is not None:
+        key, hit = "static", pose
+        rel_w2c, cam_rot = pose
+    elif not camera_grad:     # poses are constants of the mapping loop: build each frame's matrix once
         key = (id(rots_all), id(trans_all), rots_all._version, trans_all._version, int(time_idx))
         hit = _POSE_CACHE.get(key)
         if hit is not None:
             rel_w2c, cam_rot = hit
     if key is None or hit is None:
-        rot, tran = rots_all[..., time_idx], trans_all[..., time_idx]
-        if not camera_grad:
-            rot, tran = rot.detach(), tran.detach()
-        cam_rot = F.normalize(rot)
-        rel_w2c = torch.eye(4, device=dev, dtype=torch.float32)
-        rel_w2c[:3, :3] = build_rotation(cam_rot)
-        rel_w2c[:3, 3] = tran
+        rel_w2c, cam_rot = pose_matrices(params, time_idx, camera_grad)
         if key is not None:
             if len(_POSE_CACHE) > 256:
                 _POSE_CACHE.clear()
@@ -140,19 +167,21 @@ def calc_ssim(img1, img2, window_size=11):
     return (((2 * mu12 + c1) * (2 * s12 + c2)) / ((mu1_sq + mu2_sq + c1) * (s1 + s2 + c2))).mean()
 
 
-def mapping_loss(params, frame, render, loss_weights=(0.5, 1.0), ignore_outlier_depth_loss=False, fused_loss=False):
+def mapping_loss(params, frame, render, loss_weights=(0.5, 1.0), ignore_outlier_depth_loss=False, fused_loss=False,
+                 max_rendered=None):
     """SplaTAM get_loss(mapping=True): Gaussians get gradient, camera does not
     (R/scripts/splatam.py:214-347 with tracking=False, mapping=True, do_ba=False, use_l1=True).
     frame: dict(im [3,H,W], depth [1,H,W], cam settings, w2c [4,4] first-frame w2c, id time index).
     render(settings, **rendervar) -> (image, radii, depth)."""
     if fused_loss:      # fused glue: one kernel builds both rendervars (csrc/prepare.cu)
-        rv_rgb, rv_depth = fused_rendervars(params, frame["id"], frame["w2c"], camera_grad=False)
+        rv_rgb, rv_depth = fused_rendervars(params, frame["id"], frame["w2c"], camera_grad=False,
+                                            pose=frame.get("pose"))
     else:
         tg = transform_to_frame(params, frame["id"], gaussians_grad=True, camera_grad=False)
         rv_rgb, rv_depth = rgb_rendervar(params, tg), depth_sil_rendervar(params, frame["w2c"], tg)
     if fused_loss and render is default_render:      # N1: both colour sets in one raster pass
         from .rasterizer import GaussianRasterizer
-        im, depth_sil, radius, _ = GaussianRasterizer(raster_settings=frame["cam"]).forward_fused(
+        im, depth_sil, radius, _ = GaussianRasterizer(raster_settings=frame["cam"], max_rendered=max_rendered).forward_fused(
             means3D=rv_rgb["means3D"], means2D=rv_rgb["means2D"], opacities=rv_rgb["opacities"],
             colors_precomp=rv_rgb["colors_precomp"], colors_extra=rv_depth["colors_precomp"],
             scales=rv_rgb["scales"], rotations=rv_rgb["rotations"])
@@ -301,6 +330,57 @@ class ShardedMapper:
     def params(self):
         return dict(self.g.params, **self.cam)
 
+    # ---- CUDA-graph mode -----------------------------------------------------------------------------------
+    def enable_graph(self, window, slack=1.3):
+        """Capture loss forward + backward of one keyframe into a CUDA graph (sync-free rasterizer with a fixed
+        instance capacity = slack x the largest num_rendered over `window`).  Afterwards `step` copies the chosen
+        keyframe into static buffers and replays the graph: ~6 launches per step instead of ~60, and no host
+        synchronisation, so the step no longer depends on host speed.  Frames must share one camera."""
+        assert self.fused and self.g.flat.is_cuda and self.render is default_render
+        from .rasterizer import GaussianRasterizer
+        dev = self.g.flat.device
+        f0 = window[0]
+        worst = 0
+        for fr in window:            # one synchronous pass to size the capacity
+            with torch.no_grad():
+                rgb, dep = fused_rendervars(self.params(), fr["id"], fr["w2c"], camera_grad=False)
+                c, _, _ = GaussianRasterizer(fr["cam"])(**rgb)
+            worst = max(worst, _last_num_rendered())
+        self._cap = int(worst * slack) + 4096
+        self._static = dict(id=f0["id"], cam=f0["cam"], w2c=f0["w2c"].clone(), im=f0["im"].clone(), depth=f0["depth"].clone(),
+                            pose=tuple(t.clone() for t in pose_matrices(self.params(), f0["id"])))
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                self.g.zero_grad()
+                loss, radius = mapping_loss(self.params(), self._static, self.render, fused_loss=True, max_rendered=self._cap)
+                loss.backward()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self.g.flat_grad.zero_()
+            loss, radius = mapping_loss(self.params(), self._static, self.render, fused_loss=True, max_rendered=self._cap)
+            loss.backward()
+            self._g_loss, self._g_seen = loss.detach(), (radius > 0).to(torch.int32)
+        return self._cap
+
+    def _replay(self, frame):
+        st = self._static
+        st["im"].copy_(frame["im"], non_blocking=True)
+        st["depth"].copy_(frame["depth"], non_blocking=True)
+        st["w2c"].copy_(frame["w2c"], non_blocking=True)
+        rel, cr = fused_pose_cached(self.params(), frame["id"])
+        st["pose"][0].copy_(rel, non_blocking=True)
+        st["pose"][1].copy_(cr, non_blocking=True)
+        self._graph.replay()
+        return self._g_loss, self._g_seen
+
+    def check_capacity(self):
+        """(num_rendered, overflowed) of the last graph replay; synchronises.  Call occasionally."""
+        from .rasterizer import GaussianRasterizer
+        return GaussianRasterizer.last_counts()
+
     def schedule(self, window_size):
         """Keyframe index (into the window) rendered by each rank this step: a shared-seed permutation
         dealt round-robin, so ranks draw distinct keyframes whenever the window holds >= world frames."""
@@ -316,9 +396,13 @@ class ShardedMapper:
     def step(self, window):
         """One sharded mapping step over `window` (list of keyframe dicts).  Returns the mean loss."""
         picks = self.schedule(len(window))
-        self.g.zero_grad()
-        loss, radius = self.accumulate(window[picks[self.rank]])
-        seen = (radius > 0).to(torch.int32)
+        if getattr(self, "_graph", None) is not None:
+            loss, seen = self._replay(window[picks[self.rank]])
+            loss, seen = loss.clone(), seen.clone()
+        else:
+            self.g.zero_grad()
+            loss, radius = self.accumulate(window[picks[self.rank]])
+            seen = (radius > 0).to(torch.int32)
         if self.dist and self.world > 1:
             self.dist.all_reduce(self.g.flat_grad, op=self.dist.ReduceOp.SUM, group=self.group)
             self.dist.all_reduce(seen, op=self.dist.ReduceOp.MAX, group=self.group)
@@ -327,4 +411,6 @@ class ShardedMapper:
             loss = lt / self.world
         self.opt.step()
         self.step_idx += 1
+        if getattr(self, "_graph", None) is not None:
+            return loss, seen.bool(), picks       # device scalar: the graph path never synchronises
         return float(loss), seen.bool(), picks

@@ -82,6 +82,7 @@ def _settings_pack(rs, device):
 _SIZE_CACHE = {}
 _R_HINT = {}
 _LAST_ASYNC_STATE = [None]
+_LAST_SYNC_R = [0]          # num_rendered of the most recent synchronous forward
 
 
 def _sizes(lib, P, W, H, sets):
@@ -217,6 +218,7 @@ def _forward_impl(means3D, colors_precomp, opacities, scales, rotations, cov3Ds_
         if state.binning is None:
             state.binning = _ws(16, device)
         state.num_rendered = R.value
+        _LAST_SYNC_R[0] = R.value
         _R_HINT[hint_key] = R.value
         if len(_R_HINT) > 256:
             _R_HINT.clear()
