@@ -93,14 +93,15 @@ def test_graph_mode_matches_eager(cuda_device):
     eager = M.ShardedMapper(gauss, rots, trans, seed=9)
     graph = M.ShardedMapper(gauss, rots, trans, seed=9)
     cap = graph.enable_graph(frames)
-    for _ in range(3):
-        le, _, pe = eager.step(frames)
-        lg, _, pg = graph.step(frames)
-        assert pe == pg
-        assert abs(le - float(lg)) < 1e-4 * max(1.0, abs(le)), (le, float(lg))
-    n, overflow = graph.check_capacity()
-    assert not overflow and 0 < n <= cap
+    le, _, pe = eager.step(frames)
+    lg, _, pg = graph.step(frames)
+    assert pe == pg
+    assert abs(le - float(lg)) < 1e-5 * max(1.0, abs(le)), (le, float(lg))
     ge, gg = eager.g.flat_grad, graph.g.flat_grad
-    assert float((ge - gg).norm() / ge.norm()) < 1e-3
-    # (parameters are not compared: with eps = 1e-15 Adam moves an entry by ~lr whatever the gradient's size, so
-    # entries whose gradient is float-atomics noise legitimately differ between two runs)
+    assert float((ge - gg).norm() / ge.norm()) < 1e-4
+    # (parameters are not compared after the update: with eps = 1e-15 Adam moves an entry by ~lr whatever the
+    # gradient's size, so entries whose gradient is float-atomics noise legitimately differ between two runs)
+    for _ in range(3):
+        lg, seen, _ = graph.step(frames)
+    n, overflow = graph.check_capacity()
+    assert not overflow and 0 < n <= cap and bool(torch.isfinite(lg)) and bool(seen.any())
