@@ -18,7 +18,7 @@ a = ap.parse_args()
 scene, _ = bench.make_scene(a)
 dev = torch.device("cuda:0")
 Rast, Settings = bench.get_ops(a.impl)
-step, _ = bench.gpu_step_fn(scene, dev, Rast, Settings)
+step, _, _, _ = bench.gpu_step_fn(scene, dev, Rast, Settings)
 for _ in range(a.steps):
     step()
 torch.cuda.synchronize()
