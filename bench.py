@@ -156,11 +156,15 @@ def gpu_step_fn(scene, dev, Rast, Settings, graph=False):
     R = int(color.grad_fn.state.num_rendered)
     cap = int(R * 1.25) + 4096
     rast_sf = Rast(rs, max_rendered=cap)
+    # fresh leaves for the captured path: their AccumulateGrad nodes must be born on the capture side stream
+    # (the eager leaves above were first used on the default stream, which a capture may not touch)
+    inp_g = scene.inputs(dev, requires_grad=True)
+    leaves_g = [inp_g[k] for k in ["means3D", "means2D", "colors_precomp", "opacities", "scales", "rotations"]]
 
     def sync_free():
-        for t in leaves:
+        for t in leaves_g:
             t.grad = None
-        c, _, _ = rast_sf(**inp)
+        c, _, _ = rast_sf(**inp_g)
         c.backward(dL)
         return c
     side = torch.cuda.Stream(dev)
@@ -169,11 +173,11 @@ def gpu_step_fn(scene, dev, Rast, Settings, graph=False):
         for _ in range(3):
             sync_free()
     torch.cuda.current_stream(dev).wait_stream(side)
-    for t in leaves:
+    for t in leaves_g:
         t.grad = None
     cg = torch.cuda.CUDAGraph()
     with torch.cuda.graph(cg):
-        c, _, _ = rast_sf(**inp)
+        c, _, _ = rast_sf(**inp_g)
         c.backward(dL)
     info = {"mode": "sync-free operator (max_rendered=%d = 1.25 x num_rendered) replayed from a CUDA graph" % cap,
             "max_rendered": cap, "check": rast_sf.last_counts}
