@@ -180,7 +180,8 @@ def gpu_step_fn(scene, dev, Rast, Settings, graph=False):
         c, _, _ = rast_sf(**inp_g)
         c.backward(dL)
     info = {"mode": "sync-free operator (max_rendered=%d = 1.25 x num_rendered) replayed from a CUDA graph" % cap,
-            "max_rendered": cap, "check": rast_sf.last_counts}
+            "max_rendered": cap, "check": rast_sf.last_counts,
+            "keepalive": (inp_g, dL, c, cg)}     # the graph's static inputs/outputs must outlive this function
     return cg.replay, inp, eager, info
 
 
@@ -353,8 +354,8 @@ def main():
     ms = timed(step, args.steps, args.warmup, dev, dist_on)
     clocks = sampler.stop()
     if "check" in mode:
-        n_r, overflow = mode.pop("check")()
-        assert not overflow and n_r == R, "sync-free capacity overflowed: the number would be invalid"
+        n_r, overflow = mode["check"]()
+        assert not overflow and n_r == R, f"sync-free capacity check failed: num_rendered={n_r} overflow={overflow} expected={R}"
     ms_per_step = ms / args.steps
     value = world * 1000.0 / ms_per_step
 
