@@ -34,7 +34,7 @@ METRIC = "fwd+bwd renders/sec @1M Gaussians/1200x680"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "cpu"])
     ap.add_argument("--workload", default="config3", choices=["config3", "room50k", "tum3m", "config1"])
@@ -406,8 +406,11 @@ def main():
             "geometry_backward": 56 * scene.P + 36 * scene.P + 68 * scene.P,
         }
         ach = stage_bytes[top] / (stages[top] * 1e-3) / 1e9
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch of blend_backward from the committed ncu --set full
+        # capture of this exact workload (profiles/r01_blend_final_ncu_full.txt); null for any other workload
+        traffic = 212.46e6 if (args.workload == "config3" and scene.P == 1_000_000 and top == "blend_backward") else None
         line["roofline"] = dict(bound="hbm", kernel=top, achieved=ach, peak=peak, unit="GB/s", frac=ach / peak,
-                                traffic=None, peak_source=peak_src, kernel_ms=stages[top],
+                                traffic=traffic, peak_source=peak_src, kernel_ms=stages[top],
                                 algorithmic_bytes_per_launch=stage_bytes[top],
                                 render=dict(achieved=b_algo / (ms_per_step * 1e-3) / 1e9,
                                             frac=b_algo / (ms_per_step * 1e-3) / 1e9 / peak,
