@@ -282,7 +282,7 @@ def mapping_bench(dev, world, dist_on, impl, steps=8, warmup=3, P=1_000_000):
         assert not overflow, "sync-free capacity overflowed: the mapping numbers would be invalid"
     return dict(metric="mapping keyframe-iters/sec", value=world * 1000.0 / ms, unit="keyframe-iters/s",
                 ms_per_step=ms, keyframes_per_step=world, gaussians=P, width=sc.w, height=sc.h,
-                allreduce_bytes=int(mapper.g.flat_grad.numel() * 4) if world > 1 else 0,
+                allreduce_bytes=int(mapper.g.bucket.numel() * 4) if world > 1 else 0,
                 note="SplaTAM get_loss(mapping=True) + Adam per keyframe (RGB and depth/silhouette renders, L1+SSIM, "
                      "masked depth L1); NCCL all-reduce of the packed gradient bucket when n_gpus > 1")
 

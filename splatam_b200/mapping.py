@@ -278,7 +278,12 @@ class FlatGaussians:
         n = sum(math.prod(s) for s in self.shapes.values())
         dev = tensors["means3D"].device
         self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
-        self.flat_grad = torch.zeros(n, dtype=torch.float32, device=dev)
+        # ONE all-reduce bucket: [per-Gaussian gradients (n) | per-Gaussian "seen" flags as 0/1 floats (P) | loss (1)]
+        P_ = tensors["means3D"].shape[0]
+        self.bucket = torch.zeros(n + P_ + 1, dtype=torch.float32, device=dev)
+        self.flat_grad = self.bucket[:n]
+        self.seen_f = self.bucket[n:n + P_]
+        self.loss_slot = self.bucket[n + P_:]
         self.params, off = {}, 0
         for k in GAUSSIAN_KEYS:
             m = math.prod(self.shapes[k])
@@ -289,7 +294,7 @@ class FlatGaussians:
             off += m
 
     def zero_grad(self):
-        self.flat_grad.zero_()
+        self.bucket.zero_()
 
 
 def default_render(settings, **rendervar):
@@ -359,10 +364,11 @@ class ShardedMapper:
         torch.cuda.current_stream(dev).wait_stream(side)
         self._graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self._graph):
-            self.g.flat_grad.zero_()
+            self.g.bucket.zero_()
             loss, radius = mapping_loss(self.params(), self._static, self.render, fused_loss=True, max_rendered=self._cap)
             loss.backward()
-            self._g_loss, self._g_seen = loss.detach(), (radius > 0).to(torch.int32)
+            self.g.seen_f.copy_(radius > 0)
+            self.g.loss_slot.copy_(loss.detach().reshape(1))
         return self._cap
 
     def _replay(self, frame):
@@ -374,7 +380,6 @@ class ShardedMapper:
         st["pose"][0].copy_(rel, non_blocking=True)
         st["pose"][1].copy_(cr, non_blocking=True)
         self._graph.replay()
-        return self._g_loss, self._g_seen
 
     def check_capacity(self):
         """(num_rendered, overflowed) of the last graph replay; synchronises.  Call occasionally."""
@@ -396,21 +401,21 @@ class ShardedMapper:
     def step(self, window):
         """One sharded mapping step over `window` (list of keyframe dicts).  Returns the mean loss."""
         picks = self.schedule(len(window))
-        if getattr(self, "_graph", None) is not None:
-            loss, seen = self._replay(window[picks[self.rank]])
-            loss, seen = loss.clone(), seen.clone()
+        graphed = getattr(self, "_graph", None) is not None
+        if graphed:
+            self._replay(window[picks[self.rank]])
         else:
             self.g.zero_grad()
             loss, radius = self.accumulate(window[picks[self.rank]])
-            seen = (radius > 0).to(torch.int32)
+            self.g.seen_f.copy_(radius > 0)
+            self.g.loss_slot.copy_(loss.reshape(1))
         if self.dist and self.world > 1:
-            self.dist.all_reduce(self.g.flat_grad, op=self.dist.ReduceOp.SUM, group=self.group)
-            self.dist.all_reduce(seen, op=self.dist.ReduceOp.MAX, group=self.group)
-            lt = loss.clone()
-            self.dist.all_reduce(lt, op=self.dist.ReduceOp.SUM, group=self.group)
-            loss = lt / self.world
+            # ONE collective per step: gradients, seen flags (sum of 0/1 > 0 == OR) and the loss travel together
+            self.dist.all_reduce(self.g.bucket, op=self.dist.ReduceOp.SUM, group=self.group)
         self.opt.step()
         self.step_idx += 1
-        if getattr(self, "_graph", None) is not None:
-            return loss, seen.bool(), picks       # device scalar: the graph path never synchronises
-        return float(loss), seen.bool(), picks
+        seen = self.g.seen_f > 0
+        loss = self.g.loss_slot[0] / self.world
+        if graphed:
+            return loss.clone(), seen, picks      # device scalar: the graph path never synchronises
+        return float(loss), seen, picks
