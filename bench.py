@@ -427,10 +427,12 @@ def main():
                                             frac=b_algo / (ms_per_step * 1e-3) / 1e9 / peak,
                                             note="whole fwd+bwd render, B_algo of SURVEY.md 8(d)"),
                                 stage_ms={k: round(v, 4) for k, v in stages.items()})
-        line["gpu_launches"] = 6 * args.steps
-        line["config"]["gpu_launches_note"] = ("6 hand-written kernels per step (project, emit_instances, "
-                                               "ranges_records, blend_forward, blend_backward, geometry_backward); "
-                                               "CUB radix sort/scan launches and 2 memsets not counted")
+        own = 6 if args.eager else 8
+        line["gpu_launches"] = own * args.steps
+        line["config"]["gpu_launches_note"] = (
+            "%d hand-written kernels per step (project, emit_instances, ranges_records, blend_forward, blend_backward, "
+            "geometry_backward%s); CUB radix sort/scan kernels and 2 memsets not counted"
+            % (own, "" if args.eager else ", plus finalize_count and pad_tiles of the sync-free mode"))
         if rank == 0 and world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"], _, _ = cpu_oracle_run(scene)
     if not args.no_mapping:
