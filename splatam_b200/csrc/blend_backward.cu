@@ -18,7 +18,6 @@
 // the arithmetic runs in phase 2 with all 32 lanes busy.
 #include "common.cuh"
 #include "pipeline.cuh"
-#include <stdlib.h>
 
 namespace sb {
 
@@ -55,13 +54,6 @@ __device__ __forceinline__ float fast_rcp(float x) {
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return fmaf(r, fmaf(-x, r, 1.0f), r);
-}
-
-__device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
-    asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
-}
-__device__ __forceinline__ void sts_v4(uint32_t addr, float a, float b, float c, float d) {
-    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
 // Phase 2: lanes (s, part) = (lane % kQueue, lane / kQueue) sweep pixels [kQueue*part, kQueue*(part+1))
@@ -204,8 +196,7 @@ blend_backward_kernel(const uint2* __restrict__ ranges, const float4* __restrict
     float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;          // accum_rec
     float last_alpha = 0.f, lc0 = 0.f, lc1 = 0.f, lc2 = 0.f;
     int qn = 0;                                        // queued survivors (warp-uniform)
-    // shared-space addresses of this lane's queue column and of the warp's meta rows (explicit st.shared:
-    // keeps the generic->shared window arithmetic out of the inner loop)
+    // this lane's queue column and the warp's meta rows, hoisted so the inner loop only adds an offset
     float* const qw_lane = &sm.qw[warp][0][lane];
     float* const qc_lane = &sm.qc[warp][0][lane];
     float* const qr_lane = &sm.qr[NCH == 6 ? warp : 0][0][lane];

@@ -15,7 +15,6 @@
 //   3. a warp whose 32 pixels are all saturated (T < 1e-4) stops evaluating (warp-vote early-out).
 #include "common.cuh"
 #include "pipeline.cuh"
-#include <stdlib.h>
 
 namespace sb {
 
