@@ -321,11 +321,16 @@ def cpu_oracle_run(scene, budget_s=25.0):
 
 def main():
     args = parse()
+    if args.gpus > 1 and "WORLD_SIZE" not in os.environ and args.impl != "cpu":
+        # convenience: `python bench.py --gpus N` re-launches itself one rank per GPU (the driver uses torchrun)
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+               "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 400)] + sys.argv
+        sys.exit(subprocess.call(cmd))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     scene, wl_desc = make_scene(args)
-    base = dict(metric=METRIC, unit="renders/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+    base = dict(metric=METRIC, unit="renders/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
                 higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic")
 
     if args.impl == "cpu":
