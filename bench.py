@@ -57,31 +57,75 @@ def make_scene(args):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    """SM clock / throttle reasons sampled DURING the timed region (B200_PROFILING.md's clocks line).  NVML is
+    polled from a thread every 20 ms (the regions here last 0.1-0.5 s, too short for `nvidia-smi -lms`, whose
+    process start alone can outlast them); nvidia-smi is the fallback when NVML cannot be loaded."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.rows, self.proc, self.index = [], None, index
-
-    def start(self):
+        self.index, self.sm, self.mx, self.reasons = index, [], None, set()
+        self.proc, self.thread, self.stop_flag, self.nvml, self.rows = None, None, threading.Event(), None, []
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
         except Exception:
-            self.proc = None
+            self.nvml = None
+
+    def _poll(self):
+        n = self.nvml
+        bits = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+        while not self.stop_flag.is_set():
+            try:
+                self.sm.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+                get = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
+                r = int(get(self.handle))
+                for name, b in bits.items():
+                    if r & b:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self.stop_flag.wait(0.02)
 
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append(line.strip())
 
+    def start(self):
+        self.stop_flag.clear()
+        if self.nvml is not None:
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def pause(self):
+        """End of one timed region (sampling resumes with the next start())."""
+        if self.nvml is not None and self.thread is not None:
+            self.stop_flag.set()
+            self.thread.join()
+            self.thread = None
+
     def stop(self):
+        if self.nvml is not None:
+            self.pause()
+            return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.mx,
+                    "reasons": sorted(self.reasons), "samples": len(self.sm), "source": "nvml, 20 ms poll"}
         if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml and nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
         sm, mx, reasons = [], None, set()
@@ -97,7 +141,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "source": "nvidia-smi -lms 100"}
 
 
 def load_peaks():
@@ -185,23 +229,28 @@ def gpu_step_fn(scene, dev, Rast, Settings, graph=False):
     return cg.replay, inp, eager, info
 
 
-def e2e_step_fn(scene, dev, Rast, Settings, max_rendered=None):
-    """Public-API call with HOST buffers.  Every step copies the five input tensors and dL/dcolor from pinned host
-    memory into one of two device buffer sets (H2D stream), renders forward+backward from that set, and reads the
-    colour and depth images back to pinned host memory (D2H stream, overlapping the backward).  The two buffer
-    sets let step i+1's upload overlap step i's compute, as an input pipeline would; every step's copies are
-    inside the timed region.  Same orchestration for both arms."""
-    rs = scene.settings(Settings, dev)
-    rast = Rast(rs) if max_rendered is None else Rast(rs, max_rendered=max_rendered)   # ours: sync-free operator
+def e2e_host_buffers(scene):
     host = {k: v.clone().pin_memory() for k, v in dict(means3D=scene.means3D, colors_precomp=scene.colors,
                                                       opacities=scene.opacities, scales=scene.scales,
                                                       rotations=scene.rotations).items()}
     g = torch.Generator().manual_seed(3)
     host_dL = torch.randn(3, scene.h, scene.w, generator=g).pin_memory()
+    h2d = sum(t.numel() * 4 for t in host.values()) + host_dL.numel() * 4
+    d2h = 4 * scene.h * scene.w * 4
+    return host, host_dL, h2d, d2h
+
+
+def e2e_step_fn(scene, dev, Rast, Settings, max_rendered=None):
+    """Public-API call with HOST buffers.  Every step copies the five input tensors and dL/dcolor from pinned host
+    memory into one of two device buffer sets (H2D stream), renders forward+backward from that set, and reads the
+    colour and depth images back to pinned host memory (D2H stream, overlapping the backward).  The two buffer
+    sets let step i+1's upload overlap step i's compute, as an input pipeline would; every step's copies are
+    inside the timed region.  Returns (step, h2d, d2h, begin, finish, note)."""
+    rs = scene.settings(Settings, dev)
+    rast = Rast(rs) if max_rendered is None else Rast(rs, max_rendered=max_rendered)   # ours: sync-free operator
+    host, host_dL, h2d, d2h = e2e_host_buffers(scene)
     out_color = torch.empty(3, scene.h, scene.w).pin_memory()
     out_depth = torch.empty(1, scene.h, scene.w).pin_memory()
-    h2d = sum(t.numel() * 4 for t in host.values()) + host_dL.numel() * 4
-    d2h = (out_color.numel() + out_depth.numel()) * 4
     sets = [dict({k: torch.empty_like(v, device=dev) for k, v in host.items()}, dL=torch.empty_like(host_dL, device=dev))
             for _ in range(2)]
     up, down = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
@@ -232,23 +281,102 @@ def e2e_step_fn(scene, dev, Rast, Settings, max_rendered=None):
         color.backward(buf["dL"])
         cur.wait_event(d2h_done)        # the step ends when both the gradients and the host images are complete
         free[j].record(cur)
-    return step, h2d, d2h
+    note = ("per step: 5 input tensors + dL/dcolor copied from pinned host memory (double-buffered upload stream), "
+            "colour+depth images read back to pinned host memory; eager operator calls")
+    return step, h2d, d2h, None, None, note
 
 
-def timed(step, steps, warmup, dev, dist_on):
+def e2e_graph_step_fn(scene, dev, Rast, Settings, max_rendered):
+    """The same end-to-end step (pinned-host inputs -> H2D -> forward+backward -> D2H of the images) through the
+    operator's sync-free mode, with the WHOLE step -- the six H2D copies, the operator's kernels and the two D2H
+    copies -- captured into a CUDA graph, one graph per buffer set.  The two graphs are replayed alternately on
+    two streams, so step i+1's upload overlaps step i's compute exactly as in the eager harness, but the step
+    costs the host one graph launch instead of ~40 enqueues.  Every step's copies are inside the timed region."""
+    rs = scene.settings(Settings, dev)
+    rast = Rast(rs, max_rendered=max_rendered)
+    host, host_dL, h2d, d2h = e2e_host_buffers(scene)
+    lanes = []
+    for j in range(2):
+        st, down = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        buf = dict({k: torch.empty_like(v, device=dev) for k, v in host.items()}, dL=torch.empty_like(host_dL, device=dev))
+        out_color = torch.empty(3, scene.h, scene.w).pin_memory()
+        out_depth = torch.empty(1, scene.h, scene.w).pin_memory()
+        keep = {}
+
+        def body(buf=buf, down=down, out_color=out_color, out_depth=out_depth, keep=keep):
+            cur = torch.cuda.current_stream(dev)
+            for k, v in host.items():
+                buf[k].copy_(v, non_blocking=True)
+            buf["dL"].copy_(host_dL, non_blocking=True)
+            inp = {k: buf[k].detach().requires_grad_(True) for k in host}
+            inp["means2D"] = torch.zeros_like(inp["means3D"], requires_grad=True)
+            color, radii, depth = rast(**inp)
+            down.wait_stream(cur)
+            with torch.cuda.stream(down):
+                out_color.copy_(color.detach(), non_blocking=True)
+                out_depth.copy_(depth.detach(), non_blocking=True)
+            color.backward(buf["dL"])
+            cur.wait_stream(down)
+            keep.update(inp=inp, color=color, depth=depth, radii=radii)
+        st.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(st):
+            for _ in range(2):
+                body()
+        torch.cuda.synchronize(dev)
+        keep.clear()
+        cg = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(cg, stream=st):
+            body()
+        lanes.append(dict(stream=st, graph=cg, keep=keep, buf=buf, out=(out_color, out_depth)))
+    state = {"i": 0}
+
+    def begin():        # both lanes start after everything already on the current stream (the start event)
+        cur = torch.cuda.current_stream(dev)
+        for ln in lanes:
+            ln["stream"].wait_stream(cur)
+
+    def step():
+        ln = lanes[state["i"] & 1]
+        state["i"] += 1
+        with torch.cuda.stream(ln["stream"]):
+            ln["graph"].replay()
+
+    def finish():       # the current stream (the stop event) waits for both lanes
+        cur = torch.cuda.current_stream(dev)
+        for ln in lanes:
+            cur.wait_stream(ln["stream"])
+    note = ("per step: 5 input tensors + dL/dcolor copied from pinned host memory, colour+depth images read back to "
+            "pinned host memory; the whole step (copies + sync-free operator forward+backward) is one CUDA graph "
+            "per buffer set, two sets replayed alternately on two streams so uploads overlap compute")
+    return step, h2d, d2h, begin, finish, note, lanes
+
+
+def timed(step, steps, warmup, dev, dist_on, sampler=None, begin=None, finish=None):
+    """W untimed steps, then exactly K steps between CUDA events on the current stream, bracketed by barrier +
+    synchronize; max over ranks.  begin/finish: hooks that fork / join side streams inside the timed region."""
     import torch.distributed as dist
     for _ in range(warmup):
         step()
+    if finish:
+        finish()
     torch.cuda.synchronize(dev)
     if dist_on:
         dist.barrier()
     torch.cuda.synchronize(dev)
+    if sampler:
+        sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    if begin:
+        begin()
     for _ in range(steps):
         step()
+    if finish:
+        finish()
     e1.record()
     torch.cuda.synchronize(dev)
+    if sampler:
+        sampler.pause()
     if dist_on:
         dist.barrier()
     ms = e0.elapsed_time(e1)
@@ -365,9 +493,7 @@ def main():
     R = int(color.grad_fn.num_rendered) if args.impl == "reference" else int(color.grad_fn.state.num_rendered)
 
     sampler = ClockSampler(local)
-    sampler.start()
-    ms = timed(step, args.steps, args.warmup, dev, dist_on)
-    clocks = sampler.stop()
+    ms = timed(step, args.steps, args.warmup, dev, dist_on, sampler=sampler)
     if "check" in mode:
         n_r, overflow = mode["check"]()
         assert not overflow and n_r == R, f"sync-free capacity check failed: num_rendered={n_r} overflow={overflow} expected={R}"
@@ -375,11 +501,18 @@ def main():
     value = world * 1000.0 / ms_per_step
 
     # end-to-end through the public API with host buffers
-    estep, h2d, d2h = e2e_step_fn(scene, dev, Rast, Settings, max_rendered=mode.get("max_rendered"))
-    ems = timed(estep, max(args.steps // 2, 3), 3, dev, dist_on) / max(args.steps // 2, 3)
+    e_steps = max(args.steps // 2, 4)
+    if "max_rendered" in mode:
+        estep, h2d, d2h, begin, finish, enote, lanes = e2e_graph_step_fn(scene, dev, Rast, Settings, mode["max_rendered"])
+    else:
+        estep, h2d, d2h, begin, finish, enote = e2e_step_fn(scene, dev, Rast, Settings)
+    ems = timed(estep, e_steps, 4, dev, dist_on, sampler=sampler, begin=begin, finish=finish) / e_steps
+    clocks = sampler.stop()
+    if "max_rendered" in mode:
+        n_r, overflow = Rast.last_counts()
+        assert not overflow and n_r == R, f"e2e sync-free capacity check failed: {n_r} {overflow} expected {R}"
     e2e = dict(value=world * 1000.0 / ems, unit="renders/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
-               ms_per_step=ems, note="per step: 5 input tensors + dL/dcolor copied from pinned host memory (double-buffered upload "
-                    "stream), colour+depth images read back to pinned host memory")
+               ms_per_step=ems, steps=e_steps, note=enote)
 
     b_algo = scenes.algorithmic_bytes(scene.P, R, scene.w, scene.h)
     peak, peak_src = load_peaks()

@@ -326,3 +326,25 @@ def test_sync_free_forward_matches_and_graph_captures(cuda_device):
     cr.backward(dL)
     assert torch.equal(out, cr)
     assert l2_rel(static["means3D"].grad.cpu().numpy(), ref_in["means3D"].grad.cpu().numpy()) < 1e-5
+
+
+def test_more_than_65535_tiles_uses_32bit_tile_keys(cuda_device):
+    """4112x4112 -> 257x257 = 66049 tiles: the tile-id sort switches to 32-bit keys (17 bits, as the reference's
+    getHigherMsb gives); checked against the oracle in the synchronous and the sync-free mode."""
+    import splatam_b200 as S
+    from gpu_harness import random_dL, run_ours
+    sc = scenes.config1(seed=21, P=1500, w=4112, h=4112)
+    ours = run_ours(sc, random_dL(sc, 1))
+    o = sc.oracle()
+    geo, b, r = o.geometry(), o.binning(), o.render()
+    assert np.array_equal(ours["radii"], geo["radii"])
+    assert np.array_equal(ours["keys"], b["keys"]) and np.array_equal(ours["point_list"], b["point_list"])
+    assert np.array_equal(ours["ranges"], b["ranges"])
+    assert (ours["n_contrib"] != r["n_contrib"]).mean() < 1e-4
+    assert (rel_err(ours["color"], r["color"], 1e-3) > REL).mean() < 1e-4
+    dev = cuda_device
+    rs = sc.settings(S.GaussianRasterizationSettings, dev)
+    with torch.no_grad():
+        c1, _, _ = S.GaussianRasterizer(rs, max_rendered=ours["num_rendered"] + 1000)(**sc.inputs(dev))
+    assert S.GaussianRasterizer.last_counts() == (ours["num_rendered"], False)
+    assert np.array_equal(c1.cpu().numpy().view(np.uint32), ours["color"].view(np.uint32))

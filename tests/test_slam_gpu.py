@@ -48,7 +48,9 @@ def test_slim_slam_ate_and_psnr_match_reference(cuda_device):
     for k in out:
         assert ate[k] < 0.03 * travelled, (k, ate[k], travelled)       # tracks within 3 % of the path length
         assert ps[k] > 28.0, (k, ps[k])
+    # run-to-run spread of ONE implementation is already ~1.3 dB (the reference arm alone gave 32.8 and 34.1 dB on
+    # two runs: float-atomic ordering feeds a 160-step optimisation), so the arms are compared at 2 dB
     base = "reference" if "reference" in out else "plain"
     for k in out:
-        assert abs(ps[k] - ps[base]) < 0.5, (k, ps)
+        assert abs(ps[k] - ps[base]) < 2.0, (k, ps)
         assert abs(ate[k] - ate[base]) < 0.01 * travelled, (k, ate)
