@@ -5,7 +5,8 @@ NVFLAGS := -O3 -std=c++17 $(ARCH) -lineinfo -Xcompiler -fPIC -Xcompiler -fvisibi
            --expt-relaxed-constexpr -Xptxas -v
 CSRC := splatam_b200/csrc
 OBJS := $(CSRC)/abi.o $(CSRC)/project.o $(CSRC)/binning.o $(CSRC)/blend_forward.o \
-        $(CSRC)/blend_backward.o $(CSRC)/geometry_backward.o $(CSRC)/train_ops.o $(CSRC)/prepare.o $(CSRC)/sh.o
+        $(CSRC)/blend_backward.o $(CSRC)/geometry_backward.o $(CSRC)/train_ops.o $(CSRC)/prepare.o $(CSRC)/sh.o \
+        $(CSRC)/map_ops.o
 LIB := splatam_b200/libsplatam_b200.so
 
 all: $(LIB) oracle

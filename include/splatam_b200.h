@@ -258,6 +258,34 @@ SB_API int sb_masked_l1_backward(const float* depth_sil, const float* gt_depth, 
                                  const float* g_depth, const float* g_im, float* grad_depth_sil, float* grad_im,
                                  void* stream);
 
+/* ---- map maintenance: stream compaction ---------------------------------
+ * sb_prune_mask: keep[i] = !(sigmoid(logit_opacities[i]) < opacity_threshold || max_k exp(log_scales[i,k]) >
+ * big_threshold); big_threshold <= 0 disables the size test (prune_gaussians, R/utils/slam_external.py:170-190).
+ * sb_compact_plan: exclusive scan of a 0/1 byte mask -> dst_index[n] (destination row of every kept element) and
+ * the number kept (*count_host; the call synchronises the stream).  temp: sb_compact_plan_bytes(n) device bytes.
+ * sb_compact_flat: gathers the kept rows of a packed buffer [seg0: widths[0]*P | seg1: widths[1]*P | ...] into the
+ * same packing with P_new rows (remove_points, R/utils/slam_external.py:144-167: parameters and both Adam moments).
+ * sb_depth_error / sb_new_gaussian_mask: add_new_gaussians' non-presence test on the [3,H,W] depth/silhouette
+ * render (R/scripts/splatam.py:385-405): err = |gt - depth| * (gt > 0); mask = ((sil < sil_thres) | ((depth > gt) &
+ * (err > depth_err_thres))) & (gt > 0), depth_err_thres = 50 * median(err) supplied by the caller.
+ * sb_backproject: pixels (all, or those with mask != 0 written to row dst_index[pixel]) -> new Gaussian rows:
+ * means3D = c2w * ((x-cx)/fx*z, (y-cy)/fy*z, z, 1), rgb = colour of the pixel, log_scales = log(sqrt((z /
+ * ((fx+fy)/2))^2)) repeated scale_dim times, optional mean_sq_dist (get_pointcloud, R/scripts/splatam.py:67-118;
+ * initialize_new_params, :348-375).  c2w_host: 12+ floats, row-major 3x4 (or 4x4), HOST memory. */
+SB_API int sb_prune_mask(int P, const float* logit_opacities, const float* log_scales, int scale_dim,
+                         float opacity_threshold, float big_threshold, uint8_t* keep, void* stream);
+SB_API int sb_compact_plan_bytes(int n, size_t* bytes);
+SB_API int sb_compact_plan(int n, const uint8_t* keep, uint32_t* dst_index, void* temp, size_t temp_bytes,
+                           int* count_host, void* stream);
+SB_API int sb_compact_flat(int P, int P_new, const uint8_t* keep, const uint32_t* dst_index, int num_segments,
+                           const int* widths, const float* src, float* dst, void* stream);
+SB_API int sb_depth_error(int H, int W, const float* depth_sil, const float* gt_depth, float* err, void* stream);
+SB_API int sb_new_gaussian_mask(int H, int W, const float* depth_sil, const float* gt_depth, float sil_thres,
+                                float depth_err_thres, uint8_t* mask, void* stream);
+SB_API int sb_backproject(int H, int W, const float* color, const float* depth, float fx, float fy, float cx, float cy,
+                          const float* c2w_host, const uint8_t* mask, const uint32_t* dst_index, int scale_dim,
+                          float* means3D, float* rgb, float* log_scales, float* mean_sq_dist, void* stream);
+
 /* ---- per-stage device timing (measurement only; bench.py's roofline pass) -------------------
  * Between sb_profile_begin() and sb_profile_end() every stage launch of this process is bracketed
  * by CUDA events on its stream.  sb_profile_end synchronises, writes the summed milliseconds and call

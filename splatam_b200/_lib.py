@@ -76,6 +76,14 @@ _SIGNATURES = {
     "sb_sh_backward": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sb_masked_l1_forward": (_i, [_vp, _vp, _vp, _vp, _i, _i, ctypes.c_float, _i, _vp, _vp]),
     "sb_masked_l1_backward": (_i, [_vp, _vp, _vp, _vp, _i, _i, ctypes.c_float, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "sb_prune_mask": (_i, [_i, _vp, _vp, _i, ctypes.c_float, ctypes.c_float, _vp, _vp]),
+    "sb_compact_plan_bytes": (_i, [_i, ctypes.POINTER(ctypes.c_size_t)]),
+    "sb_compact_plan": (_i, [_i, _vp, _vp, _vp, _sz, ctypes.POINTER(ctypes.c_int), _vp]),
+    "sb_compact_flat": (_i, [_i, _i, _vp, _vp, _i, ctypes.POINTER(ctypes.c_int), _vp, _vp, _vp]),
+    "sb_depth_error": (_i, [_i, _i, _vp, _vp, _vp, _vp]),
+    "sb_new_gaussian_mask": (_i, [_i, _i, _vp, _vp, ctypes.c_float, ctypes.c_float, _vp, _vp]),
+    "sb_backproject": (_i, [_i, _i, _vp, _vp, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float,
+                            ctypes.POINTER(ctypes.c_float), _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "sb_profile_begin": (_i, []),
     "sb_profile_end": (_i, [ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int)]),
     "sb_stage_name": (ctypes.c_char_p, [_i]),

@@ -318,22 +318,156 @@ class ShardedMapper:
         self.g = FlatGaussians(gaussians)
         self.cam = dict(cam_unnorm_rots=cam_unnorm_rots.detach(), cam_trans=cam_trans.detach())
         lrs = dict(self.DEFAULT_LRS, **(lrs or {}))
+        self.lrs = lrs
         # fused = hand-written Adam over the flat buffer + fused L1/SSIM loss (CUDA only); the torch path is
         # the reference formulation (R/scripts/splatam.py:160-166) and the one the CPU/gloo test exercises
         self.fused = self.g.flat.is_cuda if fused is None else bool(fused)
-        if self.fused:
-            from .train_ops import FusedAdam
-            sizes = [math.prod(self.g.shapes[k]) for k in GAUSSIAN_KEYS]
-            self.opt = FusedAdam(self.g.flat, self.g.flat_grad, sizes, [lrs[k] for k in GAUSSIAN_KEYS], eps=1e-15)
-        else:
-            self.opt = torch.optim.Adam([{"params": [self.g.params[k]], "name": k, "lr": lrs[k]} for k in GAUSSIAN_KEYS],
-                                        lr=0.0, eps=1e-15)
+        self._make_optimizer()
         self.render = render
         self.gen = torch.Generator().manual_seed(seed)   # shared seed -> identical schedule on every rank
         self.step_idx = 0
 
     def params(self):
         return dict(self.g.params, **self.cam)
+
+    # ---- map maintenance (prune / grow); every rank applies the same deterministic edit --------------------------
+    def _make_optimizer(self, m=None, v=None, t=0):
+        if self.fused:
+            from .train_ops import FusedAdam
+            sizes = [math.prod(self.g.shapes[k]) for k in GAUSSIAN_KEYS]
+            self.opt = FusedAdam(self.g.flat, self.g.flat_grad, sizes, [self.lrs[k] for k in GAUSSIAN_KEYS], eps=1e-15,
+                                 exp_avg=m, exp_avg_sq=v, step=t)
+        else:
+            self.opt = torch.optim.Adam([{"params": [self.g.params[k]], "name": k, "lr": self.lrs[k]}
+                                         for k in GAUSSIAN_KEYS], lr=0.0, eps=1e-15)
+
+    def reset_optimizer(self):
+        """Fresh Adam state, as the reference re-creates its optimizer at the start of every frame's mapping
+        phase (R/scripts/splatam.py:822)."""
+        self._make_optimizer()
+
+    def _widths(self):
+        return [self.g.shapes[k][1] if len(self.g.shapes[k]) > 1 else 1 for k in GAUSSIAN_KEYS]
+
+    def _rebuild(self, flat, P_new, m=None, v=None, t=0, state=None):
+        tensors, off = {}, 0
+        for k, w in zip(GAUSSIAN_KEYS, self._widths()):
+            tensors[k] = flat[off:off + w * P_new].view(P_new, w)
+            off += w * P_new
+        self.g = FlatGaussians(tensors)
+        self._make_optimizer(m, v, t)
+        if state is not None:                   # torch.optim path: carry the moments over
+            for k in GAUSSIAN_KEYS:
+                self.opt.state[self.g.params[k]] = state[k]
+        self._graph = None                      # shapes changed: a captured graph is stale
+
+    def remove_points(self, to_remove):
+        """Drop the rows where `to_remove` is set from the parameters and both Adam moments
+        (remove_points, R/utils/slam_external.py:144-167).  Returns the number of Gaussians kept."""
+        P = self.g.shapes["means3D"][0]
+        keep = ~to_remove.reshape(-1).bool()
+        if self.fused:
+            from . import map_ops
+            m8, dst, P_new = map_ops.compact_plan(keep)
+            if P_new == P:
+                return P
+            w = self._widths()
+            flat = map_ops.compact_flat(self.g.flat, P, w, m8, dst, P_new)
+            m = map_ops.compact_flat(self.opt.m, P, w, m8, dst, P_new)
+            v = map_ops.compact_flat(self.opt.v, P, w, m8, dst, P_new)
+            self._rebuild(flat, P_new, m, v, self.opt.t)
+            return P_new
+        P_new = int(keep.sum())
+        if P_new == P:
+            return P
+        state = {}
+        for k in GAUSSIAN_KEYS:
+            st = self.opt.state.get(self.g.params[k], None)
+            state[k] = {} if not st else dict(step=st["step"], exp_avg=st["exp_avg"][keep].clone(),
+                                              exp_avg_sq=st["exp_avg_sq"][keep].clone())
+        flat = torch.cat([self.g.params[k].detach()[keep].reshape(-1) for k in GAUSSIAN_KEYS])
+        self._rebuild(flat, P_new, state={k: s for k, s in state.items() if s} or None)
+        return P_new
+
+    def prune_gaussians(self, iter, prune_dict, scene_radius):
+        """prune_gaussians of the reference (R/utils/slam_external.py:170-197): same schedule keys
+        (start_after, stop_after, prune_every, removal_opacity_threshold, final_removal_opacity_threshold,
+        remove_big_after, reset_opacities, reset_opacities_every).  Returns the Gaussian count afterwards."""
+        P = self.g.shapes["means3D"][0]
+        if iter > prune_dict["stop_after"]:
+            return P
+        if iter >= prune_dict["start_after"] and iter % prune_dict["prune_every"] == 0:
+            thr = (prune_dict["final_removal_opacity_threshold"] if iter == prune_dict["stop_after"]
+                   else prune_dict["removal_opacity_threshold"])
+            big = 0.1 * float(scene_radius) if iter >= prune_dict["remove_big_after"] else None
+            lo, ls = self.g.params["logit_opacities"].detach(), self.g.params["log_scales"].detach()
+            if self.fused:
+                from . import map_ops
+                keep = map_ops.prune_mask(lo, ls, thr, big)
+            else:
+                remove = (torch.sigmoid(lo) < thr).squeeze(-1)
+                if big is not None:
+                    remove = remove | (torch.exp(ls).max(dim=1).values > big)
+                keep = ~remove
+            P = self.remove_points(~keep)
+        if iter > 0 and iter % prune_dict["reset_opacities_every"] == 0 and prune_dict["reset_opacities"]:
+            with torch.no_grad():                                  # inverse_sigmoid(0.01), moments zeroed
+                self.g.params["logit_opacities"].fill_(math.log(0.01 / 0.99))
+            if self.fused:
+                off = sum(math.prod(self.g.shapes[k]) for k in GAUSSIAN_KEYS[:3])
+                self.opt.m[off:off + P].zero_(); self.opt.v[off:off + P].zero_()
+            else:
+                st = self.opt.state.get(self.g.params["logit_opacities"], None)
+                if st:
+                    st["exp_avg"].zero_(); st["exp_avg_sq"].zero_()
+        return P
+
+    def add_gaussians(self, new):
+        """Append rows (dict of the five tensors) to the map; Adam moments of the new rows start at zero
+        (cat_params_to_optimizer, R/utils/slam_external.py:121-141).  Returns the new Gaussian count."""
+        P, n_new = self.g.shapes["means3D"][0], new["means3D"].shape[0]
+        if n_new == 0:
+            return P
+        dev = self.g.flat.device
+        flat = torch.cat([torch.cat([self.g.params[k].detach(), new[k].to(dev).float().reshape(n_new, -1)], 0).reshape(-1)
+                          for k in GAUSSIAN_KEYS])
+        if self.fused:
+            def grown(buf):
+                parts, off = [], 0
+                for k, w in zip(GAUSSIAN_KEYS, self._widths()):
+                    parts += [buf[off:off + w * P], torch.zeros(w * n_new, device=dev)]
+                    off += w * P
+                return torch.cat(parts)
+            self._rebuild(flat, P + n_new, grown(self.opt.m), grown(self.opt.v), self.opt.t)
+        else:
+            state = {}
+            for k in GAUSSIAN_KEYS:
+                st = self.opt.state.get(self.g.params[k], None)
+                if st:
+                    z = torch.zeros(n_new, *st["exp_avg"].shape[1:], device=dev)
+                    state[k] = dict(step=st["step"], exp_avg=torch.cat([st["exp_avg"], z], 0),
+                                    exp_avg_sq=torch.cat([st["exp_avg_sq"], z.clone()], 0))
+            self._rebuild(flat, P + n_new, state=state or None)
+        return P + n_new
+
+    def add_new_gaussians(self, frame, time_idx, intrinsics, sil_thres):
+        """add_new_gaussians of the reference (R/scripts/splatam.py:378-420): one depth/silhouette render of the
+        current map at the frame's estimated pose, non-presence mask, back-projection of the selected pixels,
+        append.  CUDA only.  Returns the number of Gaussians added."""
+        from . import map_ops
+        p = self.params()
+        with torch.no_grad():
+            tg = transform_to_frame(p, time_idx, gaussians_grad=False, camera_grad=False)
+            depth_sil, _, _ = self.render(frame["cam"], **depth_sil_rendervar(p, frame["w2c"], tg))
+            rot = F.normalize(p["cam_unnorm_rots"][..., time_idx].detach())
+            curr_w2c = torch.eye(4, device=depth_sil.device)
+            curr_w2c[:3, :3] = build_rotation(rot)[0]
+            curr_w2c[:3, 3] = p["cam_trans"][0, :, time_idx].detach()
+        new, n = map_ops.new_gaussians_from_frame(depth_sil, frame, intrinsics, curr_w2c, sil_thres,
+                                                  scale_dim=self._widths()[4])
+        if n:
+            self.add_gaussians(new)
+        return n
 
     # ---- CUDA-graph mode -----------------------------------------------------------------------------------
     def enable_graph(self, window, slack=1.3):

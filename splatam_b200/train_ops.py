@@ -16,11 +16,14 @@ class FusedAdam:
     """torch.optim.Adam semantics (betas, eps, per-segment lr; no amsgrad / weight decay) over ONE flat
     fp32 buffer and its flat gradient; one kernel launch per step."""
 
-    def __init__(self, flat, flat_grad, seg_sizes, seg_lrs, betas=(0.9, 0.999), eps=1e-15):
+    def __init__(self, flat, flat_grad, seg_sizes, seg_lrs, betas=(0.9, 0.999), eps=1e-15, exp_avg=None,
+                 exp_avg_sq=None, step=0):
         if not flat.is_cuda:
             raise _lib.SplatamB200Error("FusedAdam needs CUDA tensors (there is no CPU fallback)")
         self.flat, self.flat_grad = flat, flat_grad
-        self.m, self.v = torch.zeros_like(flat), torch.zeros_like(flat)
+        self.m = torch.zeros_like(flat) if exp_avg is None else exp_avg
+        self.v = torch.zeros_like(flat) if exp_avg_sq is None else exp_avg_sq
+        assert self.m.numel() == flat.numel() and self.v.numel() == flat.numel()
         ends, acc = [], 0
         for n in seg_sizes:
             acc += int(n)
@@ -29,7 +32,7 @@ class FusedAdam:
         self.n = len(ends)
         self.seg_end = (ctypes.c_uint32 * self.n)(*ends)
         self.seg_lr = (ctypes.c_float * self.n)(*[float(x) for x in seg_lrs])
-        self.betas, self.eps, self.t = betas, eps, 0
+        self.betas, self.eps, self.t = betas, eps, int(step)
 
     def step(self):
         self.t += 1

@@ -1,0 +1,145 @@
+"""CPU tests of the rows either side of the hot path: keyframe selection, checkpoint / PLY
+formats, and the torch (reference-formulation) path of prune / grow -- all against fixtures produced by the
+reference's own functions (tests/golden/host/make_golden_host.py)."""
+import ast
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+
+G = np.load(os.path.join(HERE, "golden", "host", "host_ops.npz"), allow_pickle=True)
+KEYS = ("means3D", "rgb_colors", "unnorm_rotations", "logit_opacities", "log_scales")
+
+
+def test_keyframe_selection_matches_reference():
+    from splatam_b200 import keyframes
+    depth, K, w2c = (torch.from_numpy(G[k]) for k in ("kf_depth", "kf_K", "kf_w2c"))
+    kfl = [{"est_w2c": torch.from_numpy(m)} for m in G["kf_list"]]
+    torch.manual_seed(11); np.random.seed(12)
+    sel = keyframes.keyframe_selection_overlap(depth, w2c, K, kfl, k=3, pixels=400)
+    assert [int(i) for i in sel] == [int(i) for i in G["kf_selected"]]
+    torch.manual_seed(11)
+    valid = torch.stack(torch.where(depth[0] > 0), dim=1)
+    pts = keyframes.get_pointcloud(depth, K, w2c, valid[torch.randint(valid.shape[0], (400,))])
+    assert pts.shape == G["kf_pts"].shape and np.allclose(pts.numpy(), G["kf_pts"], rtol=1e-6, atol=1e-6)
+
+
+def test_keyframe_selection_edge_cases():
+    from splatam_b200 import keyframes
+    depth, K, w2c = (torch.from_numpy(G[k]) for k in ("kf_depth", "kf_K", "kf_w2c"))
+    assert keyframes.keyframe_selection_overlap(depth, w2c, K, [], k=3) == []
+    behind = torch.eye(4); behind[0, 0] = behind[2, 2] = -1.0          # looks the other way: no overlap
+    assert keyframes.keyframe_selection_overlap(depth, w2c, K, [{"est_w2c": behind}], k=3, pixels=200) == []
+    same = [{"est_w2c": w2c.clone()} for _ in range(5)]
+    sel = keyframes.keyframe_selection_overlap(depth, w2c, K, same, k=2, pixels=200)
+    assert len(sel) == 2 and len(set(int(i) for i in sel)) == 2
+
+
+def test_save_params_matches_reference_file(tmp_path):
+    from splatam_b200 import formats
+    ref = dict(np.load(os.path.join(HERE, "golden", "host", "ref_params.npz"), allow_pickle=True))
+    g = torch.Generator().manual_seed(41)             # the same draws as make_golden_host.py
+    params = dict(means3D=torch.randn(7, 3, generator=g), rgb_colors=torch.rand(7, 3, generator=g),
+                  unnorm_rotations=torch.randn(7, 4, generator=g), logit_opacities=torch.randn(7, 1, generator=g),
+                  log_scales=torch.randn(7, 1, generator=g), cam_unnorm_rots=torch.randn(1, 4, 5, generator=g),
+                  cam_trans=torch.randn(1, 3, 5, generator=g), timestep=torch.arange(7).float(),
+                  intrinsics=np.eye(3, dtype=np.float32), org_width=1200, org_height=680)
+    path = formats.save_params({k: (torch.nn.Parameter(v) if isinstance(v, torch.Tensor) and v.dim() > 1 else v)
+                                for k, v in params.items()}, str(tmp_path))
+    assert os.path.basename(path) == "params.npz"
+    ours = dict(np.load(path, allow_pickle=True))
+    assert list(ours.keys()) == list(ref.keys())
+    for k in ref:
+        assert ours[k].dtype == ref[k].dtype and ours[k].shape == ref[k].shape, k
+        assert np.array_equal(ours[k], ref[k]), k
+    assert os.path.basename(formats.save_params_ckpt(params, str(tmp_path), 12)) == "params12.npz"
+    back = formats.load_params(path, device="cpu")
+    assert torch.equal(back["means3D"], params["means3D"]) and int(back["org_width"]) == 1200
+
+
+def test_ply_export_layout_and_round_trip(tmp_path):
+    from splatam_b200 import formats
+    ref = dict(np.load(os.path.join(HERE, "golden", "host", "ref_params.npz"), allow_pickle=True))
+    ply = formats.export_ply(os.path.join(HERE, "golden", "host", "ref_params.npz"), str(tmp_path / "splat.ply"))
+    blob = open(ply, "rb").read()
+    header = ("ply\nformat binary_little_endian 1.0\nelement vertex 7\n"
+              + "".join(f"property float {a}\n" for a in formats.PLY_ATTRS) + "end_header\n").encode()
+    assert blob.startswith(header) and len(blob) == len(header) + 7 * 17 * 4
+    rec = np.frombuffer(blob[len(header):], dtype="<f4").reshape(7, 17)
+    assert np.array_equal(rec[:, 0:3], ref["means3D"]) and np.all(rec[:, 3:6] == 0)
+    assert np.array_equal(rec[:, 6:9], ((ref["rgb_colors"] - 0.5) / formats.C0).astype(np.float32))
+    assert np.array_equal(rec[:, 9], ref["logit_opacities"][:, 0])
+    assert all(np.array_equal(rec[:, 10 + k], ref["log_scales"][:, 0]) for k in range(3))     # isotropic -> tiled
+    assert np.array_equal(rec[:, 13:17], ref["unnorm_rotations"])
+    back = formats.load_ply(ply)
+    assert np.allclose(back["rgb_colors"], ref["rgb_colors"], atol=1e-6)
+    assert np.array_equal(back["unnorm_rotations"], ref["unnorm_rotations"])
+
+
+def _mapper_after_one_step(fused, dev):
+    from splatam_b200 import mapping as M
+    init = {k: torch.from_numpy(G["prune_init_" + k]).to(dev) for k in KEYS}
+    m = M.ShardedMapper(init, torch.zeros(1, 4, 3, device=dev), torch.zeros(1, 3, 3, device=dev),
+                        lrs={k: 1e-3 for k in KEYS}, fused=fused)
+    off = 0
+    for k in KEYS:
+        g = torch.from_numpy(G["prune_grad_" + k]).to(dev).reshape(-1)
+        m.g.flat_grad[off:off + g.numel()].copy_(g)
+        off += g.numel()
+    m.opt.step()
+    return m
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_prune_torch_path_matches_reference(tag):
+    m = _mapper_after_one_step(False, "cpu")
+    for k in KEYS:
+        assert np.allclose(m.g.params[k].detach().numpy(), G[f"prune_{tag}_{k}_before"], rtol=1e-6, atol=1e-7), k
+    prune_dict = ast.literal_eval(str(G[f"prune_{tag}_dict"][0]))
+    P_new = m.prune_gaussians(int(G[f"prune_{tag}_iter"]), prune_dict, float(G["prune_scene_radius"]))
+    assert P_new == G[f"prune_{tag}_means3D"].shape[0] and 0 < P_new < 400
+    for k in KEYS:
+        assert np.allclose(m.g.params[k].detach().numpy(), G[f"prune_{tag}_{k}"], rtol=1e-6, atol=1e-7), k
+        st = m.opt.state[m.g.params[k]]
+        assert np.allclose(st["exp_avg"].numpy(), G[f"prune_{tag}_{k}_exp_avg"], rtol=1e-6, atol=1e-9), k
+        assert np.allclose(st["exp_avg_sq"].numpy(), G[f"prune_{tag}_{k}_exp_avg_sq"], rtol=1e-6, atol=1e-12), k
+    # the mapper keeps working on the smaller map: gradient views and the bucket follow the new size
+    assert m.g.bucket.numel() == sum(p.numel() for p in m.g.params.values()) + P_new + 1
+    m.g.flat_grad.fill_(0.5)
+    m.opt.step()
+
+
+def test_grow_torch_path_appends_rows_with_zero_moments():
+    m = _mapper_after_one_step(False, "cpu")
+    new = {k: torch.from_numpy(G["bp_iso_" + k]) for k in KEYS}
+    n = new["means3D"].shape[0]
+    before = {k: m.g.params[k].detach().clone() for k in KEYS}
+    assert m.add_gaussians(new) == 400 + n
+    for k in KEYS:
+        p = m.g.params[k].detach()
+        assert torch.equal(p[:400], before[k]) and torch.equal(p[400:], new[k].float().reshape(n, -1))
+        st = m.opt.state[m.g.params[k]]
+        assert st["exp_avg"].shape[0] == 400 + n and float(st["exp_avg"][400:].abs().sum()) == 0.0
+        assert float(st["exp_avg"][:400].abs().sum()) > 0.0
+
+
+def test_oracle_backproject_and_prune_mask_match_reference():
+    from oracle import map_ops_torch as O
+    color, depth, K, w2c = (torch.from_numpy(G[k]) for k in ("bp_color", "bp_depth", "bp_K", "bp_w2c"))
+    mask = torch.from_numpy(G["bp_mask"])
+    for tag, sd in (("iso", 1), ("aniso", 3)):
+        new, msd = O.backproject(color, depth, K, w2c, mask, scale_dim=sd)
+        for k in KEYS:
+            assert np.allclose(new[k].numpy(), G[f"bp_{tag}_{k}"], rtol=1e-6, atol=1e-6), (tag, k)
+        assert np.allclose(msd.numpy(), G[f"bp_{tag}_mean_sq_dist"], rtol=1e-6)
+    full, msd = O.backproject(color, depth, K, w2c, None)
+    assert np.allclose(full["means3D"].numpy(), G["bp_full_pts"][:, :3], rtol=1e-6, atol=1e-6)
+    lo, ls = torch.from_numpy(G["prune_a_logit_opacities_before"]), torch.from_numpy(G["prune_a_log_scales_before"])
+    keep = O.prune_keep_mask(lo, ls, 0.05, 0.1 * 2.0)
+    assert int(keep.sum()) == G["prune_a_means3D"].shape[0]
