@@ -44,7 +44,7 @@ extern "C" {
 #define SB_API
 #endif
 
-#define SB_ABI_VERSION 1
+#define SB_ABI_VERSION 2
 #define SB_TILE 16 /* BLOCK_X == BLOCK_Y == 16, X/cuda_rasterizer/config.h:16-17 (part of the key contract) */
 #define SB_CHANNELS 3 /* NUM_CHANNELS, X/cuda_rasterizer/config.h:15 */
 
@@ -212,15 +212,16 @@ SB_API int sb_export_binning(const sb_settings* s, int P, int num_rendered,
 
 /* ---- per-iteration training ops around the rasterizer -----------------
  * sb_adam_step: torch.optim.Adam (no amsgrad / weight decay) over ONE flat parameter buffer whose segments
- * [seg_end[k-1], seg_end[k]) have learning rates seg_lr[k] (host arrays, <= 16 segments); replaces the
+ * [seg_end[k-1], seg_end[k]) have learning rates seg_lr[k] (host arrays, <= 16 segments; hyper-parameters are doubles, rounded to float
+ * once inside, as torch rounds its Python-float scalars); replaces the
  * multi-group optimizer.step() of R/scripts/splatam.py:160-166,869.  `step` counts from 1.
  * sb_image_loss_*: w_l1*mean|x-y| + w_ssim*(1-mean SSIM(x,y)) over [C,H,W] images with the reference's
  * 11x11 sigma-1.5 Gaussian window and zero padding (R/utils/slam_external.py:54-97, R/scripts/splatam.py:290).
  * forward writes sums[0] = sum of the SSIM map, sums[1] = sum|x-y| (device doubles) and 3*C*H*W floats of
  * partial derivatives into `work`; backward turns them into d loss / d x given the upstream scalar grad. */
 SB_API int sb_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, size_t n,
-                        const uint32_t* seg_end, const float* seg_lr, int num_segments, int step,
-                        float beta1, float beta2, float eps, void* stream);
+                        const uint32_t* seg_end, const double* seg_lr, int num_segments, int step,
+                        double beta1, double beta2, double eps, void* stream);
 SB_API size_t sb_image_loss_workspace_floats(int C, int H, int W);
 SB_API int sb_image_loss_forward(const float* x, const float* y, int C, int H, int W, float* work,
                                  double* sums, void* stream);

@@ -65,8 +65,8 @@ _SIGNATURES = {
                          _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sb_mark_visible": (_i, [_i, _vp, _vp, _vp, _vp, _vp]),
     "sb_export_geometry": (_i, [_i, _vp, _sz, _vp, _vp, _vp, _vp, _vp]),
-    "sb_adam_step": (_i, [_vp, _vp, _vp, _vp, _sz, ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_float), _i,
-                          _i, ctypes.c_float, ctypes.c_float, ctypes.c_float, _vp]),
+    "sb_adam_step": (_i, [_vp, _vp, _vp, _vp, _sz, ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_double), _i,
+                          _i, ctypes.c_double, ctypes.c_double, ctypes.c_double, _vp]),
     "sb_image_loss_workspace_floats": (_sz, [_i, _i, _i]),
     "sb_image_loss_forward": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "sb_image_loss_backward": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, ctypes.c_float, ctypes.c_float, _vp, _vp]),
@@ -109,7 +109,7 @@ def load():
         fn = getattr(lib, name)  # AttributeError if a declared symbol is not exported
         fn.restype = restype
         fn.argtypes = argtypes
-    if lib.sb_abi_version() != 1:
+    if lib.sb_abi_version() != 2:
         raise SplatamB200Error("libsplatam_b200.so ABI version mismatch")
     _lib = lib
     return lib

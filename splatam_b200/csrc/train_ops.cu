@@ -16,20 +16,20 @@ struct AdamSegs { uint32_t end[kMaxSeg]; float lr[kMaxSeg]; int n; };
 
 __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-            size_t n, AdamSegs segs, float beta1, float beta2, float eps, float bc1, float bc2_sqrt) {
+            size_t n, AdamSegs segs, float w1, float beta2, float w2, float eps, float bc2_sqrt) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    float lr = 0.f;
+    float neg_step = 0.f;            // -(lr / bias_correction1) of this element's segment
 #pragma unroll 4
     for (int k = 0; k < segs.n; ++k)
-        if (i < segs.end[k]) { lr = segs.lr[k]; break; }
+        if (i < segs.end[k]) { neg_step = segs.lr[k]; break; }
     const float gi = g[i];
-    // torch.optim.Adam single-tensor math: lerp, addcmul, sqrt / bias-correction + eps, addcdiv
-    const float mi = fmaf(gi - m[i], 1.0f - beta1, m[i]);
-    const float vi = fmaf(gi * gi, 1.0f - beta2, v[i] * beta2);
+    // torch.optim.Adam's math, op for op: lerp_(g, 1-b1); mul_(b2).addcmul_(g, g, 1-b2); sqrt / bc2_sqrt + eps; addcdiv_
+    const float mi = fmaf(w1, gi - m[i], m[i]);
+    const float vi = fmaf(w2 * gi, gi, v[i] * beta2);
     m[i] = mi; v[i] = vi;
     const float denom = sqrtf(vi) / bc2_sqrt + eps;
-    p[i] = p[i] - (lr / bc1) * (mi / denom);
+    p[i] = fmaf(neg_step, mi / denom, p[i]);
 }
 
 // ---- fused 0.8*L1 + 0.2*(1-SSIM) ----------------------------------------------------------------------
@@ -236,19 +236,21 @@ using namespace sb;
 extern "C" {
 
 SB_API int sb_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, size_t n,
-                        const uint32_t* seg_end, const float* seg_lr, int num_segments, int step, float beta1,
-                        float beta2, float eps, void* stream) {
+                        const uint32_t* seg_end, const double* seg_lr, int num_segments, int step, double beta1,
+                        double beta2, double eps, void* stream) {
     if (!params || !grads || !exp_avg || !exp_avg_sq || !seg_end || !seg_lr || num_segments < 1 ||
         num_segments > kMaxSeg || step < 1)
         return SB_ERR_BAD_ARG;
     if (n == 0) return SB_OK;
+    // scalars are formed in double and rounded to float once, as torch does with its Python-float hyper-parameters
+    const double bc1 = 1.0 - pow(beta1, step), bc2 = 1.0 - pow(beta2, step);
     AdamSegs segs;
     segs.n = num_segments;
-    for (int k = 0; k < num_segments; ++k) { segs.end[k] = seg_end[k]; segs.lr[k] = seg_lr[k]; }
-    const double bc1 = 1.0 - pow((double)beta1, step), bc2 = 1.0 - pow((double)beta2, step);
+    for (int k = 0; k < num_segments; ++k) { segs.end[k] = seg_end[k]; segs.lr[k] = (float)(-(seg_lr[k] / bc1)); }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(params, grads, exp_avg, exp_avg_sq, n, segs, beta1, beta2,
-                                                              eps, (float)bc1, (float)sqrt(bc2));
+    adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(params, grads, exp_avg, exp_avg_sq, n, segs,
+                                                              (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2),
+                                                              (float)eps, (float)sqrt(bc2));
     SB_LAUNCH_CHECK("adam_kernel");
     return SB_OK;
 }

@@ -31,7 +31,7 @@ class FusedAdam:
         assert acc == flat.numel() and len(ends) == len(seg_lrs) <= 16
         self.n = len(ends)
         self.seg_end = (ctypes.c_uint32 * self.n)(*ends)
-        self.seg_lr = (ctypes.c_float * self.n)(*[float(x) for x in seg_lrs])
+        self.seg_lr = (ctypes.c_double * self.n)(*[float(x) for x in seg_lrs])
         self.betas, self.eps, self.t = betas, eps, int(step)
 
     def step(self):

@@ -155,8 +155,8 @@ def test_non_presence_mask_and_add_new_gaussians(cuda_device):
         loss, _, _ = m.step([frame])
     assert np.isfinite(float(loss)) and float(loss) <= float(loss0) * 1.05
     P1 = m.prune_gaussians(20, dict(start_after=0, remove_big_after=0, stop_after=20, prune_every=20,
-                                    removal_opacity_threshold=0.005, final_removal_opacity_threshold=0.3,
+                                    removal_opacity_threshold=0.005, final_removal_opacity_threshold=0.6,
                                     reset_opacities=False, reset_opacities_every=500), scene_radius=3.0)
-    assert P1 <= P0 + n and getattr(m, "_graph", None) is None
+    assert 0 < P1 < P0 + n and getattr(m, "_graph", None) is None      # the opacity-0.5 newcomers go
     loss, _, _ = m.step([frame])                      # eager again after the shape change
     assert np.isfinite(float(loss))

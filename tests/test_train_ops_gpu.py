@@ -27,8 +27,9 @@ def test_fused_adam_matches_torch_adam(cuda_device):
         ref.step()
     out = torch.cat([p.detach() for p in refs])
     assert torch.allclose(flat, out, rtol=2e-5, atol=1e-7), float((flat - out).abs().max())
-    assert torch.allclose(fused.m, torch.cat([ref.state[p]["exp_avg"] for p in refs]), rtol=1e-4, atol=1e-6)
-    assert torch.allclose(fused.v, torch.cat([ref.state[p]["exp_avg_sq"] for p in refs]), rtol=1e-4, atol=1e-8)
+    # the kernel follows torch's op order with the same double->float scalar rounding: moments agree to ~1 ulp
+    assert torch.allclose(fused.m, torch.cat([ref.state[p]["exp_avg"] for p in refs]), rtol=5e-6, atol=1e-9)
+    assert torch.allclose(fused.v, torch.cat([ref.state[p]["exp_avg_sq"] for p in refs]), rtol=5e-6, atol=1e-12)
 
 
 @pytest.mark.parametrize("shape", [(3, 680, 1200), (3, 45, 97), (1, 11, 7)])
