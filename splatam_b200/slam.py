@@ -5,7 +5,8 @@ silhouette-masked L1 sums; `mapping.track_frame`) from a constant-velocity initi
 (R/scripts/splatam.py:423-444) and then `mapping_iters` keyframe-sharded mapping steps (`ShardedMapper`) over
 a sliding window of keyframes, and reports ATE-RMSE of the estimated trajectory and the PSNR of re-rendered
 keyframes -- the two end metrics the reference prints (R/utils/eval_helpers.py:23-77,569-592).
-Densification / pruning are out of scope; the map starts from a perturbed copy of the generating scene.
+By default the map starts from a perturbed copy of the generating scene; with `initialize_map` +
+`add_new_gaussians` + `prune_dict` + `select_keyframes` it is SplaTAM's full loop from RGB-D frames alone.
 """
 import math
 
@@ -37,7 +38,7 @@ def render_frame(gauss, rots, trans, t, cam, render=None):
         render = M.default_render if render is None else render
         im, _, _ = render(cam, **M.rgb_rendervar(p, tg))
         ds, _, _ = render(cam, **M.depth_sil_rendervar(p, w2c0, tg))
-    return dict(id=t, cam=cam, w2c=w2c0, im=im.clone(), depth=ds[0:1].clone())
+    return dict(id=t, cam=cam, w2c=w2c0, im=im.clone(), depth=ds[0:1].clone(), sil=ds[1:2].clone())
 
 
 def psnr(a, b):
@@ -45,17 +46,46 @@ def psnr(a, b):
     return float(20 * torch.log10(1.0 / torch.sqrt(mse)))
 
 
+def initialize_map(frame, intrinsics, scale_dim=1):
+    """Initial Gaussians = back-projection of every valid-depth pixel of the first frame
+    (initialize_first_timestep, R/scripts/splatam.py:169-208).  Returns (parameter dict, scene_radius)."""
+    from . import map_ops
+    mask = (frame["depth"][0] > 0).reshape(-1)
+    new, _ = map_ops.backproject(frame["im"], frame["depth"], intrinsics, torch.eye(4), mask=mask, scale_dim=scale_dim)
+    return new, float(frame["depth"].max()) / 3.0            # scene_radius_depth_ratio = 3 in every shipped config
+
+
+def _curr_w2c(rots, trans, t):
+    w2c = torch.eye(4, device=rots.device)
+    w2c[:3, :3] = M.build_rotation(F.normalize(rots[..., t]))[0]
+    w2c[:3, 3] = trans[0, :, t]
+    return w2c
+
+
 def run_slam(gauss_init, frames, cam, render=None, tracking_iters=20, mapping_iters=8, keyframe_every=2,
-             window=4, fused=None, seed=0):
+             window=4, fused=None, seed=0, intrinsics=None, add_new_gaussians=False, sil_thres=0.5, prune_dict=None,
+             scene_radius=None, select_keyframes=False, checkpoint_dir=None, first_frame_iters=0):
     """Tracks every frame and maps on keyframes.  gauss_init: dict of the five Gaussian tensors (the map's
-    starting point); frames: list of dict(id, cam, w2c, im, depth).  Returns dict(rots, trans, psnr, gauss)."""
+    starting point); frames: list of dict(id, cam, w2c, im, depth).  Returns dict(rots, trans, psnr, gauss).
+
+    The optional stages follow the reference's main loop (R/scripts/splatam.py:776-925): `add_new_gaussians` grows
+    the map from each mapped frame's silhouette holes before mapping, `prune_dict` prunes inside the mapping
+    iterations (prune_gaussians' schedule keys), `select_keyframes` picks the mapping window by re-projection
+    overlap (window-2 selected + the last keyframe + the current frame) instead of the last `window` keyframes,
+    `checkpoint_dir` writes params<t>.npz per mapped frame and params.npz at the end; `first_frame_iters` mapping
+    iterations run on frame 0 before tracking starts (needed when the map is a raw back-projection)."""
     dev = gauss_init["means3D"].device
     T = len(frames)
     rots = torch.zeros(1, 4, T, device=dev); rots[:, 0] = 1.0
     trans = torch.zeros(1, 3, T, device=dev)
     kw = {} if render is None else {"render": render}
     mapper = M.ShardedMapper(gauss_init, rots, trans, seed=seed, fused=fused, **kw)
-    keyframes = [frames[0]]
+    keyframes = [dict(frames[0], est_w2c=torch.eye(4, device=dev))]
+    counts = [mapper.g.shapes["means3D"][0]]
+    for it in range(first_frame_iters):       # the reference maps frame 0 before it tracks frame 1 (splatam.py:777)
+        mapper.step([keyframes[0]])
+        if prune_dict is not None:
+            mapper.prune_gaussians(it, prune_dict, scene_radius)
     for t in range(1, T):
         with torch.no_grad():           # constant-velocity initialisation (splatam.py:423-444)
             if t > 1:
@@ -70,17 +100,36 @@ def run_slam(gauss_init, frames, cam, render=None, tracking_iters=20, mapping_it
         rots, trans = params["cam_unnorm_rots"].detach(), params["cam_trans"].detach()
         mapper.cam = dict(cam_unnorm_rots=rots, cam_trans=trans)
         if t % keyframe_every == 0:
-            keyframes.append(frames[t])
-            win = keyframes[-window:]
-            for _ in range(mapping_iters):
+            cur = dict(frames[t], est_w2c=_curr_w2c(rots, trans, t))
+            if add_new_gaussians:
+                mapper.add_new_gaussians(frames[t], t, intrinsics, sil_thres)
+            if select_keyframes:
+                from .keyframes import keyframe_selection_overlap
+                sel = keyframe_selection_overlap(frames[t]["depth"], cur["est_w2c"], torch.as_tensor(intrinsics).to(dev),
+                                                 keyframes[:-1], max(window - 2, 0))
+                win = [keyframes[int(i)] for i in sel] + [keyframes[-1], cur]
+            else:
+                win = (keyframes + [cur])[-window:]
+            mapper.reset_optimizer()                          # splatam.py:822
+            for it in range(mapping_iters):
                 mapper.step(win)
+                if prune_dict is not None:
+                    mapper.prune_gaussians(it, prune_dict, scene_radius)
+            keyframes.append(cur)
+            counts.append(mapper.g.shapes["means3D"][0])
+            if checkpoint_dir is not None:
+                from . import formats
+                formats.save_params_ckpt(dict(mapper.g.params, cam_unnorm_rots=rots, cam_trans=trans), checkpoint_dir, t)
     # PSNR of the keyframes re-rendered from the final map at the estimated poses
     final = {k: v.detach() for k, v in mapper.g.params.items()}
     vals = []
     for fr in keyframes:
         est = render_frame(final, rots, trans, fr["id"], cam, render)
         vals.append(psnr(est["im"].clamp(0, 1), fr["im"].clamp(0, 1)))
-    return dict(rots=rots, trans=trans, psnr=sum(vals) / len(vals), gauss=final)
+    if checkpoint_dir is not None:
+        from . import formats
+        formats.save_params(dict(final, cam_unnorm_rots=rots, cam_trans=trans), checkpoint_dir)
+    return dict(rots=rots, trans=trans, psnr=sum(vals) / len(vals), gauss=final, counts=counts)
 
 
 def ate_rmse(rots_est, trans_est, rots_gt, trans_gt):
