@@ -447,6 +447,31 @@ def cpu_oracle_run(scene, budget_s=25.0):
                        f"(R={o.R}); C oracle, OpenMP forward + sequential backward, {dt:.2f} s"), P_s, o.R
 
 
+def cpu_bruteforce_run(scene, P_s, max_elems=16_000_000):
+    """BASELINE.json's "brute-force PyTorch alpha-composite on the host cores": the dense [P_s, pixels] float32
+    composite of oracle/bruteforce_torch.py with torch.autograd as the backward, walked over the full image in row
+    bands (pixels are independent; the Gaussian gradients accumulate across bands), on the first P_s Gaussians of
+    the workload.  Reports renders/s of that sample and (Gaussian, pixel) pair evaluations per second."""
+    from oracle import bruteforce_torch as BF
+    torch.set_num_threads(os.cpu_count() or 1)
+    names = ["means3D", "colors", "opacities", "scales", "rotations"]
+    vals = [scene.means3D[:P_s], scene.colors[:P_s], scene.opacities[:P_s], scene.scales[:P_s], scene.rotations[:P_s]]
+    leaves = [v.clone().float().requires_grad_(True) for v in vals]
+    g = torch.Generator().manual_seed(3)
+    dL = torch.randn(3, scene.h, scene.w, generator=g)
+    band = max(1, min(scene.h, max_elems // (P_s * scene.w)))
+    t0 = time.perf_counter()
+    for r0 in range(0, scene.h, band):
+        r1 = min(scene.h, r0 + band)
+        out = BF.render(*leaves, width=scene.w, height=scene.h, tanfovx=scene.w / (2 * scene.fx),
+                        tanfovy=scene.h / (2 * scene.fy), bg=scene.bg, viewmatrix=scene.view[0], projmatrix=scene.proj[0],
+                        dtype=torch.float32, rows=(r0, r1))
+        (out["color"] * dL[:, r0:r1]).sum().backward()
+    dt = time.perf_counter() - t0
+    return dict(gaussians=P_s, renders_per_s=1.0 / dt, seconds=dt, pair_evals_per_s=P_s * scene.w * scene.h / dt,
+                cores=os.cpu_count() or 1, rows_per_band=band)
+
+
 def main():
     args = parse()
     if args.gpus > 1 and "WORLD_SIZE" not in os.environ and args.impl != "cpu":
@@ -465,6 +490,8 @@ def main():
         if rank != 0:
             return
         cb, P_s, R_s = cpu_oracle_run(scene)
+        # the brute-force PyTorch composite is O(P x pixels): timed on small prefixes of the workload, never extrapolated
+        cb["bruteforce_torch"] = [cpu_bruteforce_run(scene, n) for n in (256, 1024) if n <= scene.P]
         line = dict(base, impl="cpu", value=cb["value"], ms_per_step=1000.0 / cb["value"], n_gpus=0,
                     config=dict(workload=wl_desc, sample=cb["sample"]), cpu_baseline=cb,
                     e2e=dict(value=cb["value"], unit="renders/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),

@@ -28,8 +28,11 @@ def _quat_to_rot(q):
 
 
 def render(means3D, colors, opacities, scales, rotations, *, width, height, tanfovx, tanfovy, bg,
-           viewmatrix, projmatrix, scale_modifier=1.0, means2D=None, dtype=torch.float64, chunk=None):
+           viewmatrix, projmatrix, scale_modifier=1.0, means2D=None, dtype=torch.float64, rows=None):
     """Returns dict(color [3,H,W], depth [1,H,W], final_T [H,W], n_contrib [H,W], radii [P]).
+
+    rows=(r0, r1): composite only image rows [r0, r1) (pixels are independent), returning images of height
+    r1-r0 -- lets a caller walk a large image in bands with bounded memory (bench.py's brute-force timing).
 
     viewmatrix / projmatrix: [4,4] tensors exactly as the reference stores them (w2c transposed,
     full projection transposed), i.e. p_view = p4 @ viewmatrix.
@@ -100,9 +103,11 @@ def render(means3D, colors, opacities, scales, rotations, *, width, height, tanf
     order = torch.sort(depth.detach().to(torch.float32), stable=True).indices
     order = order[visible[order]]
     n = order.numel()
-    ys, xs = torch.meshgrid(torch.arange(H, device=dev), torch.arange(W, device=dev), indexing='ij')
+    r0, r1 = (0, H) if rows is None else (int(rows[0]), int(rows[1]))
+    ys, xs = torch.meshgrid(torch.arange(r0, r1, device=dev), torch.arange(W, device=dev), indexing='ij')
     pixx, pixy = xs.reshape(-1).to(dtype), ys.reshape(-1).to(dtype)
     tilex, tiley = (xs.reshape(-1) // 16).to(dtype), (ys.reshape(-1) // 16).to(dtype)
+    H = r1 - r0                     # from here on H is the band height (outputs are band-sized)
     HW = H * W
     if n == 0:
         color = bgc[:, None].expand(3, HW).reshape(3, H, W).clone()
