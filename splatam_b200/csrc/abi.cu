@@ -94,7 +94,7 @@ __global__ void export_geometry_kernel(int P, const uint32_t* depth_key, const f
     const bool vis = tiles_touched[i] != 0u;
     if (depths) depths[i] = vis ? __uint_as_float(depth_key[i]) : 0.f;
     if (means2D) { means2D[2 * i] = vis ? geomA[i].x : 0.f; means2D[2 * i + 1] = vis ? geomA[i].y : 0.f; }
-    if (conic_opacity) reinterpret_cast<float4*>(conic_opacity)[i] = geomB[i];
+    if (conic_opacity) reinterpret_cast<float4*>(conic_opacity)[i] = vis ? geomB[i] : make_float4(0.f, 0.f, 0.f, 0.f);
     if (tt) tt[i] = tiles_touched[i];
 }
 template <typename KeyT>

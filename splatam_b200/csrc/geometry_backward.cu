@@ -25,18 +25,47 @@ geometry_backward_kernel(int P, const float* __restrict__ means3D, const float* 
                          float* __restrict__ dL_dcov3D) {
     (void)colors;
     __shared__ float vm[16], pm[16];
+    __shared__ uint16_t s_list[256];
+    __shared__ uint32_t s_wcount[8];
     if (threadIdx.x < 16) vm[threadIdx.x] = __ldg(view + threadIdx.x);
     else if (threadIdx.x < 32) pm[threadIdx.x - 16] = __ldg(proj + threadIdx.x - 16);
+    // Block-level compaction of the visible Gaussians.  Off-screen Gaussians only get zeros written; when most of
+    // the map is off-screen (a SLAM map seen from one frame) a visible lane would otherwise drag its whole warp
+    // through the ~800-instruction path below at 1/32 utilisation.  Compacted, the visible ones fill whole warps.
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int gidx = blockIdx.x * 256 + tid;
+    const bool vis = gidx < P && radii[gidx] > 0;
+    const uint32_t ball = __ballot_sync(0xffffffffu, vis);
+    if (lane == 0) s_wcount[wid] = (uint32_t)__popc(ball);
     __syncthreads();
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= P) return;
+    uint32_t base = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { const uint32_t c = s_wcount[w]; base += (w < wid) ? c : 0u; total += c; }
+    if (vis) s_list[base + __popc(ball & ((1u << lane) - 1u))] = (uint16_t)tid;
+    __syncthreads();
+    if (gidx < P && !vis) {
+        const size_t z3 = 3 * (size_t)gidx, z4 = 4 * (size_t)gidx, z6 = 6 * (size_t)gidx;
+        dL_dmeans3D[z3] = 0.f; dL_dmeans3D[z3 + 1] = 0.f; dL_dmeans3D[z3 + 2] = 0.f;
+        dL_dmeans2D[z3] = 0.f; dL_dmeans2D[z3 + 1] = 0.f; dL_dmeans2D[z3 + 2] = 0.f;
+        dL_dcolors[z3] = 0.f; dL_dcolors[z3 + 1] = 0.f; dL_dcolors[z3 + 2] = 0.f;
+        if (dL_dcolors2) { dL_dcolors2[z3] = 0.f; dL_dcolors2[z3 + 1] = 0.f; dL_dcolors2[z3 + 2] = 0.f; }
+        dL_dopacity[gidx] = 0.f;
+        if (dL_dscales) { dL_dscales[z3] = 0.f; dL_dscales[z3 + 1] = 0.f; dL_dscales[z3 + 2] = 0.f; }
+        if (dL_drot) { dL_drot[z4] = 0.f; dL_drot[z4 + 1] = 0.f; dL_drot[z4 + 2] = 0.f; dL_drot[z4 + 3] = 0.f; }
+        if (dL_dcov3D) {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) dL_dcov3D[z6 + k] = 0.f;
+        }
+    }
+    if ((uint32_t)tid >= total) return;
+    const int idx = blockIdx.x * 256 + (int)s_list[tid];        // a visible Gaussian (radii[idx] > 0)
     const size_t i3 = 3 * (size_t)idx, i4 = 4 * (size_t)idx, i6 = 6 * (size_t)idx;
 
     float gm[3] = {0.f, 0.f, 0.f}, gm2[2] = {0.f, 0.f}, gc[3] = {0.f, 0.f, 0.f}, gop = 0.f;
     float gc2[3] = {0.f, 0.f, 0.f}, gm2_out[2] = {0.f, 0.f};   // second colour set; means2D sink (first set only)
     float gs[3] = {0.f, 0.f, 0.f}, gq[4] = {0.f, 0.f, 0.f, 0.f}, gcov[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 
-    if (radii[idx] > 0) {
+    {
         const float4* arow = reinterpret_cast<const float4*>(accum + (size_t)idx * accum_stride);
         const float4 a0 = __ldg(arow), a1 = __ldg(arow + 1), a2 = __ldg(arow + 2);
         gm2[0] = a0.x; gm2[1] = a0.y;

@@ -137,20 +137,46 @@ project_kernel(int P,
     else if (threadIdx.x < 32) s_pm[threadIdx.x - 16] = __ldg(projmatrix + threadIdx.x - 16);
     __syncthreads();
 
-    const int idx = first + threadIdx.x;
-    if (idx >= P) return;
+    // Near-plane test for every Gaussian, then block-level compaction of the survivors: a Gaussian behind the camera
+    // only gets its four "culled" words written, and the projection / covariance path below runs on whole warps of
+    // survivors instead of dragging every warp through it for a few live lanes (a SLAM map seen from one frame
+    // has a large share of its Gaussians behind or beside the camera).
+    __shared__ uint16_t s_list[kProjThreads];
+    __shared__ uint32_t s_wcount[kProjThreads / 32];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int gidx = first + tid;
+    bool front = false;
+    if (gidx < P) {
+        front = xform_row(s_vm, 2, s_mean[3 * tid], s_mean[3 * tid + 1], s_mean[3 * tid + 2]) > 0.2f;
+        if (!front) {
+            // in_frustum(): a culled point with `prefiltered` set traps in the reference (auxiliary.h:156-160).
+            if (prefiltered) __trap();
+            radii[gidx] = 0;
+            depth_key[gidx] = kCulledKey;
+            tiles_touched[gidx] = 0u;
+            iota[gidx] = (uint32_t)gidx;
+        }
+    }
+    const uint32_t ball = __ballot_sync(0xffffffffu, front);
+    if (lane == 0) s_wcount[wid] = (uint32_t)__popc(ball);
+    __syncthreads();
+    uint32_t base = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < kProjThreads / 32; ++w) { const uint32_t c = s_wcount[w]; base += (w < wid) ? c : 0u; total += c; }
+    if (front) s_list[base + __popc(ball & ((1u << lane) - 1u))] = (uint16_t)tid;
+    __syncthreads();
+    if ((uint32_t)tid >= total) return;
+    const int src = (int)s_list[tid];              // this thread now owns Gaussian first + src (in front of the camera)
+    const int idx = first + src;
 
     int32_t out_radius = 0;
     uint32_t out_tiles = 0, out_key = kCulledKey;
     float4 gA = make_float4(0.f, 0.f, -1.f, -1.f), gB = make_float4(0.f, 0.f, 0.f, 0.f);
     uint2 out_rect = make_uint2(0u, 0u);
 
-    const float px = s_mean[3 * threadIdx.x], py = s_mean[3 * threadIdx.x + 1], pz = s_mean[3 * threadIdx.x + 2];
+    const float px = s_mean[3 * src], py = s_mean[3 * src + 1], pz = s_mean[3 * src + 2];
     const float depth = xform_row(s_vm, 2, px, py, pz);
-    if (depth <= 0.2f) {
-        // in_frustum(): a culled point with `prefiltered` set traps in the reference (auxiliary.h:156-160).
-        if (prefiltered) __trap();
-    } else {
+    {
         const float hom_x = xform_row(s_pm, 0, px, py, pz);
         const float hom_y = xform_row(s_pm, 1, px, py, pz);
         const float hom_w = xform_row(s_pm, 3, px, py, pz);
@@ -167,8 +193,7 @@ project_kernel(int P,
             if (rot_al16) q = __ldg(rotations + idx);
             else { const float* rp = reinterpret_cast<const float*>(rotations) + (size_t)idx * 4;
                    q = make_float4(__ldg(rp), __ldg(rp + 1), __ldg(rp + 2), __ldg(rp + 3)); }
-            c3 = cov3d_from_scale_rot(s_scale[3 * threadIdx.x], s_scale[3 * threadIdx.x + 1],
-                                      s_scale[3 * threadIdx.x + 2], scale_modifier, q);
+            c3 = cov3d_from_scale_rot(s_scale[3 * src], s_scale[3 * src + 1], s_scale[3 * src + 2], scale_modifier, q);
         }
         const float3 cov = cov2d_exact(px, py, pz, focal_x, focal_y, tan_fovx, tan_fovy, c3, s_vm);
         const float det = __fmaf_rn(cov.x, cov.z, -__fmul_rn(cov.y, cov.y));
@@ -228,10 +253,12 @@ project_kernel(int P,
     radii[idx] = out_radius;
     depth_key[idx] = out_key;
     tiles_touched[idx] = out_tiles;
-    geomA[idx] = gA;
-    geomB[idx] = gB;
-    rect[idx] = out_rect;
     iota[idx] = (uint32_t)idx;
+    if (out_tiles != 0u) {          // geomA / geomB / rect are only ever read for Gaussians that touch a tile
+        geomA[idx] = gA;
+        geomB[idx] = gB;
+        rect[idx] = out_rect;
+    }
 }
 
 __global__ void __launch_bounds__(256)
