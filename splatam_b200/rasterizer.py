@@ -68,7 +68,8 @@ def _settings_pack(rs, device):
     resolution (R/utils/recon_helpers.py:4-27) and passes the same tuple to every call.  The cache entry
     keeps the tuple alive (so ids stay unique) and is invalidated if a tensor is modified in place."""
     key = (id(rs), str(device))
-    ver = (rs.bg._version, rs.viewmatrix._version, rs.projmatrix._version)
+    ver = (rs.bg._version, rs.viewmatrix._version, rs.projmatrix._version,
+           rs.campos._version if isinstance(rs.campos, torch.Tensor) else -1)
     hit = _PACK_CACHE.get(key)
     if hit is not None and hit[0] is rs and hit[1] == ver:
         return hit[2]
@@ -271,6 +272,7 @@ class _RasterizeGaussians(torch.autograd.Function):
             H, W = int(raster_settings.image_height), int(raster_settings.image_width)
             dev = means3D.device
             ctx.empty = True
+            ctx.dev = dev
             ctx.shapes = (means3D.shape, means2D.shape, colors_precomp.shape, opacities.shape, scales.shape,
                           rotations.shape)
             # rasterize_points.cu:67-75,81: P == 0 returns the zero-filled images without launching
@@ -304,7 +306,7 @@ class _RasterizeGaussians(torch.autograd.Function):
     def backward(ctx, grad_out_color, _grad_radii, _grad_depth):
         # depth carries no gradient (the reference drops it, __init__.py:88)
         if ctx.empty:
-            z = [torch.zeros(s) for s in ctx.shapes]
+            z = [torch.zeros(s, device=ctx.dev) for s in ctx.shapes]
             return z[0], z[1], None, z[2], z[3], z[4], z[5], None, None, None
         radii, *saved = ctx.saved_tensors
         g_means3D, g_means2D, g_colors, g_opac, g_scales, g_rot, g_cov3D = _backward_impl(

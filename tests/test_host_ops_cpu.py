@@ -143,3 +143,26 @@ def test_oracle_backproject_and_prune_mask_match_reference():
     lo, ls = torch.from_numpy(G["prune_a_logit_opacities_before"]), torch.from_numpy(G["prune_a_log_scales_before"])
     keep = O.prune_keep_mask(lo, ls, 0.05, 0.1 * 2.0)
     assert int(keep.sum()) == G["prune_a_means3D"].shape[0]
+
+
+def test_operator_api_without_gaussians_needs_no_device():
+    """P == 0: the reference returns zero images and R = 0 without launching (X/rasterize_points.cu:67-81); so does
+    the host mirror, on any device, and the (empty) gradients come back on the inputs' device.  Both argument-check
+    exceptions of the reference API fire before anything else."""
+    import splatam_b200 as S
+    rs = S.GaussianRasterizationSettings(8, 12, 1.0, 1.0, torch.zeros(3), 1.0, torch.eye(4)[None], torch.eye(4)[None], 0,
+                                         torch.zeros(3), False)
+    z = lambda *s: torch.zeros(*s, requires_grad=True)
+    inp = dict(means3D=z(0, 3), means2D=z(0, 3), opacities=z(0, 1), colors_precomp=z(0, 3), scales=z(0, 3), rotations=z(0, 4))
+    color, radii, depth = S.GaussianRasterizer(rs)(**inp)
+    assert color.shape == (3, 8, 12) and depth.shape == (1, 8, 12) and radii.shape == (0,) and radii.dtype == torch.int32
+    assert float(color.detach().abs().sum()) == 0.0
+    color.sum().backward()
+    assert inp["means3D"].grad.shape == (0, 3) and inp["rotations"].grad.shape == (0, 4)
+    with pytest.raises(Exception, match="excatly one of either SHs or precomputed colors"):
+        S.GaussianRasterizer(rs)(means3D=z(1, 3), means2D=z(1, 3), opacities=z(1, 1), scales=z(1, 3), rotations=z(1, 4))
+    with pytest.raises(Exception, match="scale/rotation pair or precomputed 3D covariance"):
+        S.GaussianRasterizer(rs)(means3D=z(1, 3), means2D=z(1, 3), opacities=z(1, 1), colors_precomp=z(1, 3))
+    with pytest.raises(S.SplatamB200Error, match="no CPU fallback"):
+        S.GaussianRasterizer(rs)(means3D=z(1, 3), means2D=z(1, 3), opacities=z(1, 1), colors_precomp=z(1, 3),
+                                 scales=z(1, 3), rotations=z(1, 4))
