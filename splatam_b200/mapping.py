@@ -87,15 +87,31 @@ def depth_sil_rendervar(params, w2c, tg):
 _POSE_CACHE = {}
 
 
+def _pose_cache_get(rots_all, trans_all, time_idx):
+    """Cache of (rel_w2c, cam_rot) per (pose tensors, their versions, frame).  Keys use id(): every entry holds weak
+    references to the two tensors and is only honoured while both are the very same live objects, so a recycled
+    id can never return another tensor's pose."""
+    key = (id(rots_all), id(trans_all), rots_all._version, trans_all._version, int(time_idx))
+    hit = _POSE_CACHE.get(key)
+    if hit is not None and hit[0]() is rots_all and hit[1]() is trans_all:
+        return key, hit[2]
+    return key, None
+
+
+def _pose_cache_put(key, rots_all, trans_all, value):
+    import weakref
+    if len(_POSE_CACHE) > 256:
+        _POSE_CACHE.clear()
+    _POSE_CACHE[key] = (weakref.ref(rots_all), weakref.ref(trans_all), value)
+
+
 def fused_pose_cached(params, time_idx):
     """Cached (rel_w2c, cam_rot) of a frame whose pose is not being optimised."""
     rots_all, trans_all = params["cam_unnorm_rots"], params["cam_trans"]
-    key = (id(rots_all), id(trans_all), rots_all._version, trans_all._version, int(time_idx))
-    hit = _POSE_CACHE.get(key)
+    key, hit = _pose_cache_get(rots_all, trans_all, time_idx)
     if hit is None:
-        if len(_POSE_CACHE) > 256:
-            _POSE_CACHE.clear()
-        hit = _POSE_CACHE[key] = pose_matrices(params, time_idx)
+        hit = pose_matrices(params, time_idx)
+        _pose_cache_put(key, rots_all, trans_all, hit)
     return hit
 
 
@@ -123,21 +139,12 @@ def fused_rendervars(params, time_idx, w2c0, camera_grad, pose=None):
     from .prepare import prepare_gaussians
     rots_all, trans_all = params["cam_unnorm_rots"], params["cam_trans"]
     dev = params["means3D"].device
-    key = hit = None
     if pose is not None:
-        key, hit = "static", pose
         rel_w2c, cam_rot = pose
     elif not camera_grad:     # poses are constants of the mapping loop: build each frame's matrix once
-        key = (id(rots_all), id(trans_all), rots_all._version, trans_all._version, int(time_idx))
-        hit = _POSE_CACHE.get(key)
-        if hit is not None:
-            rel_w2c, cam_rot = hit
-    if key is None or hit is None:
+        rel_w2c, cam_rot = fused_pose_cached(params, time_idx)
+    else:
         rel_w2c, cam_rot = pose_matrices(params, time_idx, camera_grad)
-        if key is not None:
-            if len(_POSE_CACHE) > 256:
-                _POSE_CACHE.clear()
-            _POSE_CACHE[key] = (rel_w2c, cam_rot)
     means_cam, rots, opac, sc3, dcols = prepare_gaussians(params["means3D"], params["unnorm_rotations"],
                                                           params["logit_opacities"], params["log_scales"], rel_w2c,
                                                           cam_rot, w2c0)

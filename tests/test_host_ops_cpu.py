@@ -166,3 +166,20 @@ def test_operator_api_without_gaussians_needs_no_device():
     with pytest.raises(S.SplatamB200Error, match="no CPU fallback"):
         S.GaussianRasterizer(rs)(means3D=z(1, 3), means2D=z(1, 3), opacities=z(1, 1), colors_precomp=z(1, 3),
                                  scales=z(1, 3), rotations=z(1, 4))
+
+
+def test_pose_cache_follows_tensor_identity_and_version():
+    from splatam_b200 import mapping as M
+    rots = torch.zeros(1, 4, 3); rots[:, 0] = 1.0
+    trans = torch.zeros(1, 3, 3)
+    p = dict(means3D=torch.zeros(1, 3), cam_unnorm_rots=rots, cam_trans=trans)
+    a = M.fused_pose_cached(p, 1)
+    assert M.fused_pose_cached(p, 1) is a                      # same tensors, same versions -> cached
+    trans[0, 0, 1] = 0.25                                      # in-place edit bumps the version
+    b = M.fused_pose_cached(p, 1)
+    assert b is not a and float(b[0][0, 3]) == 0.25
+    p2 = dict(p, cam_trans=trans.clone())                      # another tensor object: never served from the cache
+    c = M.fused_pose_cached(p2, 1)
+    assert c is not b and torch.equal(c[0], b[0])
+    ref = M.pose_matrices(p, 1)
+    assert torch.equal(ref[0], b[0]) and torch.equal(ref[1], b[1])
