@@ -92,3 +92,38 @@ def test_flat_bucket_layout_and_schedule():
     loss.backward()
     assert m.g.flat_grad.abs().sum() > 0 and torch.isfinite(m.g.flat_grad).all()
     assert m.schedule(5)[0] in range(5)
+
+
+def _worker_edit(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(2)
+    gauss, rots, trans, frames = _problem()
+    mapper = M.ShardedMapper(gauss, rots, trans, render=_cpu_render, seed=123)
+    mapper.step(frames)
+    prune = dict(start_after=0, remove_big_after=0, stop_after=20, prune_every=1, removal_opacity_threshold=0.25,
+                 final_removal_opacity_threshold=0.25, reset_opacities=False, reset_opacities_every=500)
+    P1 = mapper.prune_gaussians(1, prune, scene_radius=50.0)          # every rank prunes its (identical) replica
+    g = torch.Generator().manual_seed(9)
+    new = dict(means3D=torch.randn(7, 3, generator=g) * 0.3 + torch.tensor([0.0, 0.0, 2.5]),
+               rgb_colors=torch.rand(7, 3, generator=g), unnorm_rotations=torch.tensor([[1.0, 0, 0, 0]]).repeat(7, 1),
+               logit_opacities=torch.zeros(7, 1), log_scales=torch.full((7, 1), -3.5))
+    P2 = mapper.add_gaussians(new)
+    loss, seen, picks = mapper.step(frames)                           # all-reduce over the RESIZED bucket
+    q.put((rank, P1, P2, mapper.g.bucket.numel(), mapper.g.flat.detach().numpy().copy(), loss))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_prune_and_grow_keep_replicas_identical():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_edit, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = sorted([q.get(timeout=300) for _ in range(2)], key=lambda t: t[0])
+    [p.join(60) for p in procs]
+    (_, P1a, P2a, nb_a, flat_a, la), (_, P1b, P2b, nb_b, flat_b, lb) = res
+    assert P1a == P1b and 0 < P1a < 96 and P2a == P2b == P1a + 7
+    assert nb_a == nb_b == P2a * 12 + P2a + 1                         # gradients | seen flags | loss
+    assert (flat_a == flat_b).all() and abs(la - lb) < 1e-7
