@@ -55,6 +55,27 @@ def test_bad_arguments_are_rejected_before_any_launch():
     assert lib.sb_forward_geometry(ctypes.byref(s), 0, None, None, None, None, None, None, None, 0,
                                    ctypes.byref(R), None) == 0 and R.value == 0    # P == 0 fast path
     assert lib.sb_mark_visible(-1, None, None, None, None, None) == 1
+    # map-maintenance and training entry points: every argument check comes before the first CUDA call
+    assert lib.sb_prune_mask(-1, None, None, 1, 0.5, 0.0, None, None) == 1
+    assert lib.sb_prune_mask(4, 1, 1, 2, 0.5, 0.0, 1, None) == 1            # scale_dim must be 1 or 3
+    assert lib.sb_prune_mask(0, None, None, 1, 0.5, 0.0, None, None) == 0   # empty map: nothing to do
+    n = ctypes.c_int(7)
+    assert lib.sb_compact_plan(-1, None, None, None, 0, ctypes.byref(n), None) == 1
+    assert lib.sb_compact_plan(0, None, None, None, 0, ctypes.byref(n), None) == 0 and n.value == 0
+    assert lib.sb_compact_plan(5, None, None, None, 0, ctypes.byref(n), None) == 1
+    w = (ctypes.c_int * 2)(3, 0)
+    assert lib.sb_compact_flat(4, 2, 1, 1, 2, w, 1, 1, None) == 1          # zero-width segment
+    assert lib.sb_compact_flat(4, 5, 1, 1, 1, w, 1, 1, None) == 1          # P_new > P
+    assert lib.sb_compact_flat(4, 2, 1, 1, 0, w, 1, 1, None) == 1          # no segments
+    assert lib.sb_new_gaussian_mask(0, 8, 1, 1, 0.5, 1.0, 1, None) == 1
+    assert lib.sb_depth_error(8, 8, None, 1, 1, None) == 1
+    c2w = (ctypes.c_float * 16)()
+    assert lib.sb_backproject(8, 8, 1, 1, 1.0, 1.0, 0.0, 0.0, c2w, 1, None, 1, 1, 1, 1, None, None) == 1   # mask without plan
+    assert lib.sb_backproject(8, 8, 1, 1, 1.0, 1.0, 0.0, 0.0, c2w, None, None, 2, 1, 1, 1, None, None) == 1  # scale_dim
+    lr = (ctypes.c_double * 1)(1e-3)
+    end = (ctypes.c_uint32 * 1)(4)
+    assert lib.sb_adam_step(1, 1, 1, 1, 4, end, lr, 1, 0, 0.9, 0.999, 1e-15, None) == 1                      # step counts from 1
+    assert lib.sb_adam_step(1, 1, 1, 1, 4, end, lr, 17, 1, 0.9, 0.999, 1e-15, None) == 1                     # > 16 segments
 
 
 def test_operator_argument_checks_match_reference():
