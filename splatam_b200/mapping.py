@@ -337,6 +337,27 @@ class ShardedMapper:
     def params(self):
         return dict(self.g.params, **self.cam)
 
+    # ---- what stays single-GPU: rank `src` does it, the result is broadcast ---------------------
+    def sync_camera(self, src=0):
+        """Tracking runs on one rank (its backward uses float atomics, so two ranks would not end bit-identical);
+        the estimated poses are broadcast so every replica maps with the same cameras."""
+        if self.dist and self.world > 1:
+            for k in ("cam_unnorm_rots", "cam_trans"):
+                t = self.cam[k].detach().clone().contiguous()
+                self.dist.broadcast(t, src=src, group=self.group)
+                self.cam[k] = t
+        return self.cam
+
+    def broadcast_frame(self, frame, src=0):
+        """A keyframe's images are loaded by one rank and broadcast once when the keyframe is created (13 MB at
+        1200x680); `frame` must hold tensors of the right shape on every rank (contents are overwritten)."""
+        if self.dist and self.world > 1:
+            for k in ("im", "depth", "w2c"):
+                t = frame[k].contiguous()
+                self.dist.broadcast(t, src=src, group=self.group)
+                frame[k] = t
+        return frame
+
     # ---- map maintenance (prune / grow); every rank applies the same deterministic edit --------------------------
     def _make_optimizer(self, m=None, v=None, t=0):
         if self.fused:

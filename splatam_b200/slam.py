@@ -99,6 +99,8 @@ def run_slam(gauss_init, frames, cam, render=None, tracking_iters=20, mapping_it
         M.track_frame(params, frames[t], render=render, num_iters=tracking_iters, fused=fused)
         rots, trans = params["cam_unnorm_rots"].detach(), params["cam_trans"].detach()
         mapper.cam = dict(cam_unnorm_rots=rots, cam_trans=trans)
+        cam_now = mapper.sync_camera()            # multi-rank runs: rank 0's tracking result is the pose of record
+        rots, trans = cam_now["cam_unnorm_rots"], cam_now["cam_trans"]
         if t % keyframe_every == 0:
             cur = dict(frames[t], est_w2c=_curr_w2c(rots, trans, t))
             if add_new_gaussians:

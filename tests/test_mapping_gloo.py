@@ -127,3 +127,34 @@ def test_prune_and_grow_keep_replicas_identical():
     assert P1a == P1b and 0 < P1a < 96 and P2a == P2b == P1a + 7
     assert nb_a == nb_b == P2a * 12 + P2a + 1                         # gradients | seen flags | loss
     assert (flat_a == flat_b).all() and abs(la - lb) < 1e-7
+
+
+def _worker_sync(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    gauss, rots, trans, frames = _problem()
+    mapper = M.ShardedMapper(gauss, rots, trans, render=_cpu_render, seed=5)
+    mapper.cam = dict(cam_unnorm_rots=rots + 0.1 * rank, cam_trans=trans - 0.2 * rank)    # rank 1 "tracked" differently
+    cam = mapper.sync_camera(src=0)
+    fr = dict(frames[0], im=frames[0]["im"] + rank, depth=frames[0]["depth"] * (1 + rank), w2c=torch.eye(4) * (1 + rank))
+    fr = mapper.broadcast_frame(fr, src=0)
+    q.put((rank, cam["cam_unnorm_rots"].numpy().copy(), cam["cam_trans"].numpy().copy(), fr["im"].numpy().copy(),
+           fr["depth"].numpy().copy(), fr["w2c"].numpy().copy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_single_rank_results_are_broadcast():
+    """Tracking / data loading stay on one rank; poses and keyframe images reach the others by broadcast."""
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_sync, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = sorted([q.get(timeout=300) for _ in range(2)], key=lambda t: t[0])
+    [p.join(60) for p in procs]
+    gauss, rots, trans, frames = _problem()
+    for a, b in zip(res[0][1:], res[1][1:]):
+        assert (a == b).all()
+    assert (res[1][1] == rots.numpy()).all() and (res[1][2] == trans.numpy()).all()
+    assert (res[1][3] == frames[0]["im"].numpy()).all() and (res[1][5] == torch.eye(4).numpy()).all()
