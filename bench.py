@@ -539,7 +539,9 @@ def main():
         n_r, overflow = Rast.last_counts()
         assert not overflow and n_r == R, f"e2e sync-free capacity check failed: {n_r} {overflow} expected {R}"
     e2e = dict(value=world * 1000.0 / ems, unit="renders/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
-               ms_per_step=ems, steps=e_steps, note=enote)
+               ms_per_step=ems, steps=e_steps, note=enote,
+               # the copies are real: sustained host<->device rate they imply per GPU (PCIe Gen5 x16 ~ 55 GB/s per direction)
+               h2d_gbs=h2d / (ems * 1e-3) / 1e9, d2h_gbs=d2h / (ems * 1e-3) / 1e9)
 
     b_algo = scenes.algorithmic_bytes(scene.P, R, scene.w, scene.h)
     peak, peak_src = load_peaks()
