@@ -11,6 +11,21 @@ namespace sb {
 
 namespace {
 
+// Block-wide copy of n staged floats to dst[off .. off+n): 16-byte stores when the destination is 16-byte aligned
+// (off is a multiple of 256 rows, so only the array base decides), scalar stores for the tail / unaligned bases.
+__device__ __forceinline__ void copy_out(float* __restrict__ dst, const float* __restrict__ stage, size_t off, int n,
+                                         int tid) {
+    float* d = dst + off;
+    int done = 0;
+    if ((reinterpret_cast<uintptr_t>(d) & 15u) == 0u) {
+        const int n4 = n >> 2;
+        for (int i = tid; i < n4; i += 256)
+            reinterpret_cast<float4*>(d)[i] = reinterpret_cast<const float4*>(stage)[i];
+        done = n4 << 2;
+    }
+    for (int i = done + tid; i < n; i += 256) d[i] = stage[i];
+}
+
 __global__ void __launch_bounds__(256)
 geometry_backward_kernel(int P, const float* __restrict__ means3D, const float* __restrict__ colors,
                          const float* __restrict__ scales, const float* __restrict__ rotations,
@@ -43,29 +58,33 @@ geometry_backward_kernel(int P, const float* __restrict__ means3D, const float* 
     for (int w = 0; w < 8; ++w) { const uint32_t c = s_wcount[w]; base += (w < wid) ? c : 0u; total += c; }
     if (vis) s_list[base + __popc(ball & ((1u << lane) - 1u))] = (uint16_t)tid;
     __syncthreads();
+    // Outputs are staged in shared memory (one slot per Gaussian of the block) and written out by the whole block
+    // with contiguous 16-byte stores: the per-thread AoS stores (3-6 strided scalar stores per array) cost ~3x the
+    // L2 write transactions of the bytes they move, and this kernel is store-bound when most Gaussians are culled.
+    __shared__ __align__(16) float s_o3[5][768];      // means3D, means2D, colors, colors2, scales
+    __shared__ __align__(16) float s_rot[1024];
+    __shared__ __align__(16) float s_cov[1536];
+    __shared__ __align__(16) float s_op[256];
     if (gidx < P && !vis) {
-        const size_t z3 = 3 * (size_t)gidx, z4 = 4 * (size_t)gidx, z6 = 6 * (size_t)gidx;
-        dL_dmeans3D[z3] = 0.f; dL_dmeans3D[z3 + 1] = 0.f; dL_dmeans3D[z3 + 2] = 0.f;
-        dL_dmeans2D[z3] = 0.f; dL_dmeans2D[z3 + 1] = 0.f; dL_dmeans2D[z3 + 2] = 0.f;
-        dL_dcolors[z3] = 0.f; dL_dcolors[z3 + 1] = 0.f; dL_dcolors[z3 + 2] = 0.f;
-        if (dL_dcolors2) { dL_dcolors2[z3] = 0.f; dL_dcolors2[z3 + 1] = 0.f; dL_dcolors2[z3 + 2] = 0.f; }
-        dL_dopacity[gidx] = 0.f;
-        if (dL_dscales) { dL_dscales[z3] = 0.f; dL_dscales[z3 + 1] = 0.f; dL_dscales[z3 + 2] = 0.f; }
-        if (dL_drot) { dL_drot[z4] = 0.f; dL_drot[z4 + 1] = 0.f; dL_drot[z4 + 2] = 0.f; dL_drot[z4 + 3] = 0.f; }
+#pragma unroll
+        for (int a = 0; a < 5; ++a) { s_o3[a][3 * tid] = 0.f; s_o3[a][3 * tid + 1] = 0.f; s_o3[a][3 * tid + 2] = 0.f; }
+        s_rot[4 * tid] = 0.f; s_rot[4 * tid + 1] = 0.f; s_rot[4 * tid + 2] = 0.f; s_rot[4 * tid + 3] = 0.f;
+        s_op[tid] = 0.f;
         if (dL_dcov3D) {
 #pragma unroll
-            for (int k = 0; k < 6; ++k) dL_dcov3D[z6 + k] = 0.f;
+            for (int k = 0; k < 6; ++k) s_cov[6 * tid + k] = 0.f;
         }
     }
-    if ((uint32_t)tid >= total) return;
-    const int idx = blockIdx.x * 256 + (int)s_list[tid];        // a visible Gaussian (radii[idx] > 0)
+    const bool has_work = (uint32_t)tid < total;
+    const int src = has_work ? (int)s_list[tid] : 0;
+    const int idx = blockIdx.x * 256 + src;                     // a visible Gaussian (radii[idx] > 0) when has_work
     const size_t i3 = 3 * (size_t)idx, i4 = 4 * (size_t)idx, i6 = 6 * (size_t)idx;
 
     float gm[3] = {0.f, 0.f, 0.f}, gm2[2] = {0.f, 0.f}, gc[3] = {0.f, 0.f, 0.f}, gop = 0.f;
     float gc2[3] = {0.f, 0.f, 0.f}, gm2_out[2] = {0.f, 0.f};   // second colour set; means2D sink (first set only)
     float gs[3] = {0.f, 0.f, 0.f}, gq[4] = {0.f, 0.f, 0.f, 0.f}, gcov[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 
-    {
+    if (has_work) {
         const float4* arow = reinterpret_cast<const float4*>(accum + (size_t)idx * accum_stride);
         const float4 a0 = __ldg(arow), a1 = __ldg(arow + 1), a2 = __ldg(arow + 2);
         gm2[0] = a0.x; gm2[1] = a0.y;
@@ -201,17 +220,31 @@ geometry_backward_kernel(int P, const float* __restrict__ means3D, const float* 
         }
     }
 
-    dL_dmeans3D[i3] = gm[0]; dL_dmeans3D[i3 + 1] = gm[1]; dL_dmeans3D[i3 + 2] = gm[2];
-    dL_dmeans2D[i3] = gm2_out[0]; dL_dmeans2D[i3 + 1] = gm2_out[1]; dL_dmeans2D[i3 + 2] = 0.f;
-    dL_dcolors[i3] = gc[0]; dL_dcolors[i3 + 1] = gc[1]; dL_dcolors[i3 + 2] = gc[2];
-    if (dL_dcolors2) { dL_dcolors2[i3] = gc2[0]; dL_dcolors2[i3 + 1] = gc2[1]; dL_dcolors2[i3 + 2] = gc2[2]; }
-    dL_dopacity[idx] = gop;
-    if (dL_dscales) { dL_dscales[i3] = gs[0]; dL_dscales[i3 + 1] = gs[1]; dL_dscales[i3 + 2] = gs[2]; }
-    if (dL_drot) { dL_drot[i4] = gq[0]; dL_drot[i4 + 1] = gq[1]; dL_drot[i4 + 2] = gq[2]; dL_drot[i4 + 3] = gq[3]; }
-    if (dL_dcov3D) {
+    if (has_work) {
+        float* o;
+        o = &s_o3[0][3 * src]; o[0] = gm[0]; o[1] = gm[1]; o[2] = gm[2];
+        o = &s_o3[1][3 * src]; o[0] = gm2_out[0]; o[1] = gm2_out[1]; o[2] = 0.f;
+        o = &s_o3[2][3 * src]; o[0] = gc[0]; o[1] = gc[1]; o[2] = gc[2];
+        o = &s_o3[3][3 * src]; o[0] = gc2[0]; o[1] = gc2[1]; o[2] = gc2[2];
+        o = &s_o3[4][3 * src]; o[0] = gs[0]; o[1] = gs[1]; o[2] = gs[2];
+        o = &s_rot[4 * src]; o[0] = gq[0]; o[1] = gq[1]; o[2] = gq[2]; o[3] = gq[3];
+        s_op[src] = gop;
+        if (dL_dcov3D) {
 #pragma unroll
-        for (int k = 0; k < 6; ++k) dL_dcov3D[i6 + k] = gcov[k];
+            for (int k = 0; k < 6; ++k) s_cov[6 * src + k] = gcov[k];
+        }
     }
+    __syncthreads();
+    const int rows = min(256, P - blockIdx.x * 256);
+    const size_t row0 = (size_t)blockIdx.x * 256;
+    copy_out(dL_dmeans3D, s_o3[0], row0 * 3, rows * 3, tid);
+    copy_out(dL_dmeans2D, s_o3[1], row0 * 3, rows * 3, tid);
+    copy_out(dL_dcolors, s_o3[2], row0 * 3, rows * 3, tid);
+    if (dL_dcolors2) copy_out(dL_dcolors2, s_o3[3], row0 * 3, rows * 3, tid);
+    if (dL_dscales) copy_out(dL_dscales, s_o3[4], row0 * 3, rows * 3, tid);
+    if (dL_drot) copy_out(dL_drot, s_rot, row0 * 4, rows * 4, tid);
+    copy_out(dL_dopacity, s_op, row0, rows, tid);
+    if (dL_dcov3D) copy_out(dL_dcov3D, s_cov, row0 * 6, rows * 6, tid);
 }
 
 }  // namespace

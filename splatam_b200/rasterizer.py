@@ -244,7 +244,7 @@ def _backward_impl(state, saved, radii, grad_out_color, grad_out_color2=None):
         have_sr = scales is not None and scales.numel() != 0
         g_scales = e(P, 3) if have_sr else torch.zeros((P, 3), dtype=torch.float32, device=device)
         g_rot = e(P, 4) if have_sr else torch.zeros((P, 4), dtype=torch.float32, device=device)
-        g_cov3D = e(P, 6)
+        g_cov3D = None if have_sr else e(P, 6)     # only the cov3D_precomp branch has a consumer for it
         g_colors2 = e(P, 3) if sets == 2 else None
         grad_out_color2 = _f32c(grad_out_color2, "grad_out_color2") if sets == 2 else None
         W_, H_ = int(pack.c.image_width), int(pack.c.image_height)
