@@ -387,42 +387,83 @@ def timed(step, steps, warmup, dev, dist_on, sampler=None, begin=None, finish=No
     return ms
 
 
-def mapping_bench(dev, world, dist_on, impl, steps=8, warmup=3, P=1_000_000):
-    """Secondary BASELINE metric: mapping keyframe-iterations/sec.  One iteration = SplaTAM's
-    get_loss(mapping=True) (2 raster fwd + 2 raster bwd + glue) + one Adam step; a K-rank step renders K
-    keyframes (one per GPU), all-reduces the packed per-Gaussian gradient bucket over NCCL and applies the
-    same Adam update on every rank.  Synthetic Replica-sized room, isotropic Gaussians."""
-    from splatam_b200 import mapping as M
-    Rast, Settings = get_ops(impl)
-    sc = scenes.room(seed=4, P=P)
+def mapping_problem(dev, Settings, P, nframes=8):
+    """The mapping workload: a view-filling SplaTAM-style map (scenes.view_filling: one Gaussian per pixel of a
+    1200x680 frame + back-projections of later keyframes, every Gaussian in view, R ~ 2.3 P) and `nframes` keyframes
+    at slightly different poses."""
+    sc = scenes.view_filling(seed=12, P=P)
     cam = sc.settings(Settings, dev)
     g = torch.Generator().manual_seed(0)
     gauss = dict(means3D=sc.means3D, rgb_colors=sc.colors, unnorm_rotations=sc.rotations,
                  logit_opacities=torch.logit(sc.opacities.clamp(0.02, 0.98)), log_scales=torch.log(sc.scales[:, :1]))
-    gauss = {k: v.to(dev) for k, v in gauss.items()}
-    nframes = 8
+    gauss = {k: v.to(dev).contiguous() for k, v in gauss.items()}
     rots = torch.zeros(1, 4, nframes); rots[:, 0] = 1.0
-    rots[:, 1:] = 0.005 * torch.randn(1, 3, nframes, generator=g)
-    trans = 0.02 * torch.randn(1, 3, nframes, generator=g)
+    rots[:, 1:] = 0.002 * torch.randn(1, 3, nframes, generator=g)
+    trans = 0.01 * torch.randn(1, 3, nframes, generator=g)
+    vv, uu = torch.meshgrid(torch.arange(sc.h, dtype=torch.float32), torch.arange(sc.w, dtype=torch.float32), indexing="ij")
+    depth = scenes._surface_depth(uu, vv)[None]
     frames = [dict(id=t, cam=cam, w2c=torch.eye(4, device=dev), im=torch.rand(3, sc.h, sc.w, generator=g).to(dev),
-                   depth=(1.0 + 2.0 * torch.rand(1, sc.h, sc.w, generator=g)).to(dev)) for t in range(nframes)]
-    # the reference arm keeps the stock two-call render and the PyTorch glue / Adam / SSIM: none of this repo's
-    # kernels on it; ours uses the fused glue + fused two-set render + fused loss + fused Adam
+                   depth=(depth * (1.0 + 0.01 * torch.randn(1, sc.h, sc.w, generator=g))).to(dev)) for t in range(nframes)]
+    return sc, gauss, rots.to(dev), trans.to(dev), frames
+
+
+def mapping_bench(dev, world, dist_on, impl, steps=50, warmup=5, P=1_000_000):
+    """Secondary BASELINE metric: mapping keyframe-iterations/sec.  One iteration = SplaTAM's
+    get_loss(mapping=True) (2 raster fwd + 2 raster bwd + glue + L1/SSIM) + one Adam step.
+    ours: a K-rank step renders K keyframes (one per GPU), all-reduces the packed per-Gaussian gradient bucket over
+    NCCL and applies the same fused Adam update on every rank.
+    reference: the STOCK mapping inner loop of R/scripts/splatam.py:828-885 -- the unmodified get_loss (:214-347),
+    transform_to_frame / rendervars (R/utils/slam_helpers.py), calc_ssim (R/utils/slam_external.py) and
+    initialize_optimizer (:160-166), imported from baseline/_ref/SplaTAM, over the unmodified reference extension;
+    single GPU (the reference has no multi-GPU path), so its value is per process."""
+    Rast, Settings = get_ops(impl)
+    sc, gauss, rots, trans, frames = mapping_problem(dev, Settings, P)
+    note = ("SplaTAM get_loss(mapping=True) + Adam per keyframe (RGB and depth/silhouette renders, L1+SSIM, masked depth "
+            "L1) on a view-filling map (scenes.view_filling: every Gaussian in view)")
     if impl == "ours":
-        mapper = M.ShardedMapper(gauss, rots.to(dev), trans.to(dev), seed=11, fused=True)
+        from splatam_b200 import mapping as M
+        mapper = M.ShardedMapper(gauss, rots, trans, seed=11, fused=True)
         mapper.enable_graph(frames)       # loss fwd+bwd of a keyframe as one CUDA graph over the sync-free rasterizer
-    else:
-        render = (lambda settings, **rv: Rast(raster_settings=settings)(**rv))
-        mapper = M.ShardedMapper(gauss, rots.to(dev), trans.to(dev), render=render, seed=11, fused=False)
-    ms = timed(lambda: mapper.step(frames), steps, warmup, dev, dist_on) / steps
-    if impl == "ours":
+        ms = timed(lambda: mapper.step(frames), steps, warmup, dev, dist_on) / steps
         n_r, overflow = mapper.check_capacity()
         assert not overflow, "sync-free capacity overflowed: the mapping numbers would be invalid"
-    return dict(metric="mapping keyframe-iters/sec", value=world * 1000.0 / ms, unit="keyframe-iters/s",
-                ms_per_step=ms, keyframes_per_step=world, gaussians=P, width=sc.w, height=sc.h,
-                allreduce_bytes=int(mapper.g.bucket.numel() * 4) if world > 1 else 0,
-                note="SplaTAM get_loss(mapping=True) + Adam per keyframe (RGB and depth/silhouette renders, L1+SSIM, "
-                     "masked depth L1); NCCL all-reduce of the packed gradient bucket when n_gpus > 1")
+        visible = int((mapper.g.seen_f > 0).sum().item())
+        out = dict(value=world * 1000.0 / ms, keyframes_per_step=world, num_rendered=int(n_r), visible=visible,
+                   allreduce_bytes=int(mapper.g.bucket.numel() * 4) if world > 1 else 0, impl_note=note +
+                   "; fused glue + fused two-set render + fused loss + fused Adam, step replayed from a CUDA graph; "
+                   "NCCL all-reduce of the packed gradient bucket when n_gpus > 1")
+        out.update(mapper.timing_breakdown(frames) if hasattr(mapper, "timing_breakdown") else {})
+    else:
+        import refsrc
+        if not refsrc.available():
+            return {"unavailable": "reference Python (baseline/_ref/SplaTAM) not installed"}
+        R = refsrc.load(reference_extension())
+        params = {k: torch.nn.Parameter(v.clone().contiguous()) for k, v in dict(gauss, cam_unnorm_rots=rots, cam_trans=trans).items()}
+        lrs = dict(means3D=0.0001, rgb_colors=0.0025, unnorm_rotations=0.001, logit_opacities=0.05, log_scales=0.001,
+                   cam_unnorm_rots=0.0, cam_trans=0.0)                 # R/configs/replica/splatam.py:92-100
+        opt = R.splatam.initialize_optimizer(params, lrs, tracking=False)
+        variables = dict(max_2D_radius=torch.zeros(sc.P, device=dev), means2D_gradient_accum=torch.zeros(sc.P, device=dev),
+                         denom=torch.zeros(sc.P, device=dev))
+        rng = np.random.RandomState(11)
+        stats = {}
+
+        def step():
+            fr = frames[rng.randint(0, len(frames))]
+            data = dict(cam=fr["cam"], im=fr["im"], depth=fr["depth"], id=fr["id"], intrinsics=None, w2c=fr["w2c"],
+                        iter_gt_w2c_list=None)
+            loss, var, losses = R.splatam.get_loss(params, data, variables, fr["id"], dict(im=0.5, depth=1.0), False, 0.5,
+                                                   True, False, mapping=True)
+            loss.backward()
+            with torch.no_grad():
+                opt.step()
+                opt.zero_grad(set_to_none=True)
+            stats["seen"] = var["seen"]
+        ms = timed(step, steps, warmup, dev, dist_on) / steps
+        out = dict(value=1000.0 / ms, keyframes_per_step=1, visible=int(stats["seen"].sum().item()), allreduce_bytes=0,
+                   impl_note=note + "; stock get_loss / initialize_optimizer of R/scripts/splatam.py imported unmodified, "
+                   "reference extension, eager PyTorch; per process (the reference maps on one GPU)")
+    return dict(dict(metric="mapping keyframe-iters/sec", unit="keyframe-iters/s", ms_per_step=ms, steps=steps, warmup=warmup,
+                     gaussians=P, width=sc.w, height=sc.h, workload=sc.name), **out)
 
 
 def cpu_oracle_run(scene, budget_s=25.0):

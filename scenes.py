@@ -150,6 +150,51 @@ def room(seed=1, P=50_000, cam=REPLICA, anisotropic=False, w2c=None):
     return Scene("room_%d" % P, w, h, fx, fy, cx, cy, pts, col, opac, scales, q, w2c=w2c)
 
 
+def _surface_depth(u, v):
+    """Smooth synthetic depth map (metres) standing in for a Replica / TUM depth frame."""
+    return 2.5 + 0.8 * torch.sin(u / 130.0) * torch.cos(v / 90.0) + 0.3 * torch.sin(u / 23.0 + v / 31.0)
+
+
+def view_filling(seed=12, cam=REPLICA, P=None, stride=1, anisotropic=False, w2c=None, opacity=(0.45, 0.6)):
+    """A map that FILLS the view the way SplaTAM's maps do: one Gaussian per pixel of the first frame,
+    back-projected through the depth map, sigma_world = depth / f (one pixel std on screen), logit opacity ~ 0
+    (R/scripts/splatam.py:67-118,120-157,196-203: get_pointcloud + initialize_params with the "projective"
+    mean_sq_dist), plus -- when P exceeds the pixel count -- further Gaussians at random sub-pixel positions of the
+    same surface with sizes 0.8-1.3 px, standing in for the back-projections that later keyframes add
+    (R/scripts/splatam.py:378-420).  Every Gaussian is in view, so num_rendered ~ 2 x P and every tile list is
+    hundreds of entries long -- unlike `room`, where ~97 % of the Gaussians lie outside the frustum."""
+    g = torch.Generator().manual_seed(seed)
+    w, h, fx, fy, cx, cy = cam["w"], cam["h"], cam["fx"], cam["fy"], cam["cx"], cam["cy"]
+    vv, uu = torch.meshgrid(torch.arange(0, h, stride, dtype=torch.float32), torch.arange(0, w, stride, dtype=torch.float32),
+                            indexing="ij")
+    u, v = uu.reshape(-1), vv.reshape(-1)
+    n_grid = u.numel()
+    P = n_grid if P is None else int(P)
+    if P < n_grid:
+        keep = torch.randperm(n_grid, generator=g)[:P].sort().values
+        u, v = u[keep], v[keep]
+        size = torch.ones(P)
+    else:
+        extra = P - n_grid
+        u = torch.cat([u, w * _rand(g, extra)])
+        v = torch.cat([v, h * _rand(g, extra)])
+        size = torch.cat([torch.ones(n_grid), 0.8 + 0.5 * _rand(g, extra)])
+    z = _surface_depth(u, v) * (1.0 + 0.004 * torch.randn(P, generator=g))
+    means = torch.stack([(u - cx) * z / fx, (v - cy) * z / fy, z], 1)
+    base = size * z / ((fx + fy) / 2.0)
+    if anisotropic:
+        scales = base[:, None] * (0.5 + 1.0 * _rand(g, P, 3))
+        q = torch.randn(P, 4, generator=g)
+        q = q / q.norm(dim=1, keepdim=True)
+    else:
+        scales = base[:, None].repeat(1, 3)
+        q = torch.zeros(P, 4)
+        q[:, 0] = 1.0
+    opac = opacity[0] + (opacity[1] - opacity[0]) * _rand(g, P)
+    col = 0.5 + 0.5 * torch.sin(means * 6.0 + torch.tensor([0.0, 2.0, 4.0]))
+    return Scene("view_filling_%d" % P, w, h, fx, fy, cx, cy, means, col, opac, scales, q, w2c=w2c)
+
+
 def edge_cases(seed=5, w=97, h=45):
     """Ragged image size (not a multiple of 16), Gaussians behind / on the near plane, far off-screen,
     huge and sub-pixel splats, opacity below 1/255, exact depth ties, non-zero background, and a

@@ -242,8 +242,9 @@ def tracking_loss(params, frame, render, sil_thres=0.99, loss_weights=(0.5, 1.0)
         uncertainty = (depth_sil[2:3] - depth ** 2).detach()
         mask = (frame["depth"] > 0) & (~torch.isnan(depth)) & (~torch.isnan(uncertainty)) & (sil > sil_thres)
         mask = mask.detach()
-        l_depth = (torch.abs(frame["depth"] - depth) * mask).sum()
-        l_im = (torch.abs(frame["im"] - im) * mask).sum()          # mask broadcast over the 3 channels
+        # boolean indexing, as the reference: a NaN depth under a cleared mask bit must not reach the sum
+        l_depth = torch.abs(frame["depth"] - depth)[mask].sum()
+        l_im = torch.abs(frame["im"] - im)[torch.tile(mask, (3, 1, 1))].sum()
     return loss_weights[0] * l_im + loss_weights[1] * l_depth, radius
 
 
