@@ -53,7 +53,9 @@ typedef enum sb_status {
     SB_ERR_BAD_ARG = 1,      /* null/negative/inconsistent argument                     */
     SB_ERR_WORKSPACE = 2,    /* a caller-provided workspace is too small                */
     SB_ERR_CUDA = 3,         /* a CUDA runtime call or kernel launch failed             */
-    SB_ERR_UNSUPPORTED = 4   /* feature of the reference API not built  */
+    SB_ERR_UNSUPPORTED = 4,  /* feature of the reference API not built  */
+    SB_ERR_BINNING_TOO_SMALL = 5 /* sb_forward only: stage 1 is complete and *num_rendered is set, but the guessed
+                                binning workspace cannot hold it -- finish with sb_forward_render_ex */
 } sb_status;
 
 /* Mirror of GaussianRasterizationSettings (X/diff_gaussian_rasterization/__init__.py:134-145).
@@ -135,7 +137,7 @@ SB_API int sb_backward(const sb_settings* s, int P, int num_rendered,
  * sb_forward_geometry + sb_forward_render_ex back to back WITHOUT returning to the caller between them, so
  * the GPU is idle only for the num_rendered read-back itself.  The caller passes a binning workspace sized
  * from a guess (e.g. the previous call's num_rendered plus slack); if it is too small the call returns
- * SB_ERR_WORKSPACE with *num_rendered set and stage 1 complete -- the caller then allocates
+ * SB_ERR_BINNING_TOO_SMALL with *num_rendered set and stage 1 complete -- the caller then allocates
  * sb_binning_workspace_bytes_ex(*num_rendered, ...) and finishes with sb_forward_render_ex. */
 SB_API int sb_forward(const sb_settings* s, int P, const float* means3D, const float* opacities, const float* scales,
                const float* rotations, const float* cov3D_precomp, const float* colors, const float* colors2,
@@ -148,7 +150,8 @@ SB_API int sb_forward(const sb_settings* s, int P, const float* means3D, const f
  * instances) for the binning workspace (sb_binning_workspace_bytes_ex(capacity, ...)); unused slots are padded
  * with a sentinel tile id and sorted to the end.  No memcpy to the host, no synchronisation, no allocation:
  * the call (and sb_backward_ex with num_rendered := capacity) can be captured into a CUDA graph.
- * If the scene needs more than `capacity` instances the overflow flag is set and the images are incomplete;
+ * If the scene needs more than `capacity` instances the overflow flag (geometry workspace, int32 word 2) is set and
+ * the images are written as NaN, so a truncated render cannot pass for a valid one;
  * sb_read_counts (which synchronises) returns the true count and the flag so the caller can grow and redo. */
 SB_API int sb_forward_async(const sb_settings* s, int P, const float* means3D, const float* opacities,
                      const float* scales, const float* rotations, const float* cov3D_precomp, const float* colors,
@@ -222,6 +225,14 @@ SB_API int sb_export_binning(const sb_settings* s, int P, int num_rendered,
 SB_API int sb_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, size_t n,
                         const uint32_t* seg_end, const double* seg_lr, int num_segments, int step,
                         double beta1, double beta2, double eps, void* stream);
+/* Guarded step for the sync-free (CUDA-graph) mapping loop: the step count and the bias-correction scalars live in a
+ * device-side clock (`clock_dev`: sb_adam_clock_bytes() bytes, zero-initialised = step 0; first int = steps applied,
+ * second int = steps skipped), and when `skip_if_nonzero` points at a non-zero device float the whole update is a
+ * no-op -- used with the rasterizer's instance-capacity overflow flag, whose gradients are incomplete. */
+SB_API size_t sb_adam_clock_bytes(void);
+SB_API int sb_adam_step_guarded(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, size_t n,
+                                const uint32_t* seg_end, const double* seg_lr, int num_segments, void* clock_dev,
+                                const float* skip_if_nonzero, double beta1, double beta2, double eps, void* stream);
 SB_API size_t sb_image_loss_workspace_floats(int C, int H, int W);
 SB_API int sb_image_loss_forward(const float* x, const float* y, int C, int H, int W, float* work,
                                  double* sums, void* stream);

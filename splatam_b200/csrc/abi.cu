@@ -122,6 +122,7 @@ SB_API const char* sb_status_string(int status) {
         case SB_ERR_WORKSPACE: return "SB_ERR_WORKSPACE";
         case SB_ERR_CUDA: return "SB_ERR_CUDA";
         case SB_ERR_UNSUPPORTED: return "SB_ERR_UNSUPPORTED";
+        case SB_ERR_BINNING_TOO_SMALL: return "SB_ERR_BINNING_TOO_SMALL";
         default: return "SB_ERR_UNKNOWN";
     }
 }
@@ -190,7 +191,7 @@ SB_API int sb_forward(const sb_settings* s, int P, const float* means3D, const f
     size_t need = 0;
     rc = sb_binning_workspace_bytes_ex(*num_rendered, s->image_width, s->image_height, colors2 ? 2 : 1, &need);
     if (rc != SB_OK) return rc;
-    if (*num_rendered > 0 && (binning_ws == nullptr || binning_ws_bytes < need)) return SB_ERR_WORKSPACE;
+    if (*num_rendered > 0 && (binning_ws == nullptr || binning_ws_bytes < need)) return SB_ERR_BINNING_TOO_SMALL;
     return sb_forward_render_ex(s, P, *num_rendered, colors, colors2, geom_ws, geom_ws_bytes, binning_ws,
                                 binning_ws_bytes, image_ws, image_ws_bytes, out_color, out_color2, out_depth, stream);
 }
@@ -219,7 +220,7 @@ SB_API int sb_forward_async(const sb_settings* s, int P, const float* means3D, c
     if ((rc = launch_depth_order(P, g, st)) != SB_OK) return rc;
     if ((rc = launch_finalize_count(P, g, capacity, st)) != SB_OK) return rc;
     if ((rc = launch_binning(*s, P, capacity, colors, colors2, g, b, img, g.header, st)) != SB_OK) return rc;
-    return launch_blend_forward(*s, capacity, g, b, img, out_color, out_color2, out_depth, st);
+    return launch_blend_forward(*s, capacity, g, b, img, out_color, out_color2, out_depth, g.header + 2, st);
 }
 
 SB_API int sb_read_counts(const void* geom_ws, size_t geom_ws_bytes, int P, int* num_rendered, int* overflow,
@@ -263,7 +264,7 @@ SB_API int sb_forward_render_ex(const sb_settings* s, int P, int num_rendered, c
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     int rc = launch_binning(*s, P, num_rendered, colors, colors2, g, b, img, nullptr, st);
     if (rc != SB_OK) return rc;
-    return launch_blend_forward(*s, num_rendered, g, b, img, out_color, out_color2, out_depth, st);
+    return launch_blend_forward(*s, num_rendered, g, b, img, out_color, out_color2, out_depth, nullptr, st);
 }
 
 SB_API int sb_backward(const sb_settings* s, int P, int num_rendered, const float* means3D, const float* colors,

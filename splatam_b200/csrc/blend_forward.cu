@@ -46,7 +46,7 @@ blend_forward_kernel(const uint2* __restrict__ ranges, const float4* __restrict_
                      const float* __restrict__ bg, float* __restrict__ out_color,
                      float* __restrict__ out_color2,
                      float* __restrict__ out_depth, float* __restrict__ final_T,
-                     uint32_t* __restrict__ n_contrib) {
+                     uint32_t* __restrict__ n_contrib, const int32_t* __restrict__ overflow_flag) {
     __shared__ FwdSmem<NCH> sm;
     const uint32_t tile = blockIdx.x;
     const uint2 range = ranges[tile];
@@ -150,6 +150,9 @@ blend_forward_kernel(const uint2* __restrict__ ranges, const float4* __restrict_
 
     if (inside) {
         const size_t pix = (size_t)py * W + px, hw = (size_t)H * W;
+        // sync-free mode: if the scene needed more tile instances than the caller's capacity, the lists are truncated;
+        // poison the images so that an incomplete render can never be mistaken for a valid one
+        if (overflow_flag != nullptr && __ldg(overflow_flag) != 0) { C0 = C1 = C2 = E0 = E1 = E2 = __int_as_float(0x7fc00000); }
         final_T[pix] = T;
         n_contrib[pix] = last;
         out_color[pix] = __fmaf_rn(__ldg(bg), T, C0);
@@ -168,7 +171,7 @@ blend_forward_kernel(const uint2* __restrict__ ranges, const float4* __restrict_
 
 int launch_blend_forward(const sb_settings& s, int R, const GeometryWs& g, const BinningWs& b,
                          const ImageWs& img, float* out_color, float* out_color2, float* out_depth,
-                         cudaStream_t st) {
+                         const int32_t* overflow_flag, cudaStream_t st) {
     (void)R;
     const int W = s.image_width, H = s.image_height;
     const uint32_t gx = (W + kTile - 1) / kTile, gy = (H + kTile - 1) / kTile;
@@ -177,12 +180,12 @@ int launch_blend_forward(const sb_settings& s, int R, const GeometryWs& g, const
         blend_forward_kernel<6, 4><<<gx * gy, kBlendThreads, 0, st>>>(img.ranges, b.recA, b.recB, b.recC, b.recD,
                                                                       g.depth_key, W, H, gx, s.bg, out_color,
                                                                       out_color2, out_depth, img.final_T,
-                                                                      img.n_contrib);
+                                                                      img.n_contrib, overflow_flag);
     else
         blend_forward_kernel<3, 5><<<gx * gy, kBlendThreads, 0, st>>>(img.ranges, b.recA, b.recB, b.recC, nullptr,
                                                                       g.depth_key, W, H, gx, s.bg, out_color,
                                                                       nullptr, out_depth, img.final_T,
-                                                                      img.n_contrib);
+                                                                      img.n_contrib, overflow_flag);
     SB_LAUNCH_CHECK("blend_forward_kernel");
     return SB_OK;
 }

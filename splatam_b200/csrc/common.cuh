@@ -52,7 +52,7 @@ struct Carver {
 // geomB = {conic.x, conic.y, conic.z, opacity}
 // rect  = {xmin | ymin<<16, xmax | ymax<<16} tile rectangle (getRect, auxiliary.h:46-56)
 struct GeometryWs {
-    int32_t*  header;        // [0]=num_rendered  [1]=num_visible (device)
+    int32_t*  header;        // [0]=num_rendered  [1]=num_visible  [2]=capacity overflow flag of the sync-free mode (device)
     uint32_t* depth_key;     // [P] float bits of view-space z, kCulledKey if it emits nothing
     uint32_t* tiles_touched; // [P]
     float4*   geomA;         // [P]
@@ -119,9 +119,11 @@ int launch_binning(const sb_settings& s, int P, int R, const float* colors, cons
                    const GeometryWs& g, const BinningWs& b, const ImageWs& img, const int32_t* count_dev,
                    cudaStream_t st);
 int launch_finalize_count(int P, const GeometryWs& g, int capacity, cudaStream_t st);
+// overflow_flag != nullptr (sync-free mode): device int that is non-zero when the instance lists were truncated; the
+// images are then written as NaN
 int launch_blend_forward(const sb_settings& s, int R, const GeometryWs& g, const BinningWs& b,
                          const ImageWs& img, float* out_color, float* out_color2, float* out_depth,
-                         cudaStream_t st);
+                         const int32_t* overflow_flag, cudaStream_t st);
 int launch_blend_backward(const sb_settings& s, int R, const BinningWs& b, const ImageWs& img,
                           const float* dL_dout_color, const float* dL_dout_color2, float* accum,
                           cudaStream_t st);

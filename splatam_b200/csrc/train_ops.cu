@@ -14,15 +14,36 @@ namespace {
 constexpr int kMaxSeg = 16;
 struct AdamSegs { uint32_t end[kMaxSeg]; float lr[kMaxSeg]; int n; };
 
+// Device-resident optimizer clock of the guarded step: the step count only advances on steps that are applied, and the
+// bias-correction scalars are formed from it on the device (one thread), so a skipped step leaves NO trace.
+struct AdamClock { int t; int skipped; float bc2_sqrt; float neg_step[kMaxSeg]; };
+struct AdamLrs { double lr[kMaxSeg]; int n; };
+
+__global__ void adam_clock_kernel(AdamClock* __restrict__ clk, const float* __restrict__ skip_if_nonzero, AdamLrs segs,
+                                  double beta1, double beta2) {
+    if (skip_if_nonzero != nullptr && *skip_if_nonzero != 0.f) { clk->skipped += 1; return; }
+    const int t = clk->t + 1;
+    clk->t = t;
+    const double bc1 = 1.0 - pow(beta1, (double)t), bc2 = 1.0 - pow(beta2, (double)t);
+    clk->bc2_sqrt = (float)sqrt(bc2);
+    for (int k = 0; k < segs.n; ++k) clk->neg_step[k] = (float)(-(segs.lr[k] / bc1));   // as sb_adam_step forms it
+}
+
+// GUARDED == true: the per-segment step sizes and bc2_sqrt come from the device clock and the whole update is a no-op
+// when *skip_if_nonzero != 0 (the sync-free rasterizer overflowed its instance capacity: gradients are incomplete).
+template <bool GUARDED>
 __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-            size_t n, AdamSegs segs, float w1, float beta2, float w2, float eps, float bc2_sqrt) {
+            size_t n, AdamSegs segs, float w1, float beta2, float w2, float eps, float bc2_sqrt,
+            const AdamClock* __restrict__ clk, const float* __restrict__ skip_if_nonzero) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    if (GUARDED && skip_if_nonzero != nullptr && *skip_if_nonzero != 0.f) return;
+    if (GUARDED) bc2_sqrt = clk->bc2_sqrt;
     float neg_step = 0.f;            // -(lr / bias_correction1) of this element's segment
 #pragma unroll 4
     for (int k = 0; k < segs.n; ++k)
-        if (i < segs.end[k]) { neg_step = segs.lr[k]; break; }
+        if (i < segs.end[k]) { neg_step = GUARDED ? clk->neg_step[k] : segs.lr[k]; break; }
     const float gi = g[i];
     // torch.optim.Adam's math, op for op: lerp_(g, 1-b1); mul_(b2).addcmul_(g, g, 1-b2); sqrt / bc2_sqrt + eps; addcdiv_
     const float mi = fmaf(w1, gi - m[i], m[i]);
@@ -35,14 +56,16 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
 // ---- fused 0.8*L1 + 0.2*(1-SSIM) ----------------------------------------------------------------------
 constexpr int kTW = 32, kTH = 8, kR = 5, kWin = 11;     // output tile 32x8, 11-tap separable Gaussian
 constexpr int kPW = kTW + 2 * kR, kPH = kTH + 2 * kR;   // padded tile 42 x 18
-__constant__ float c_gauss[kWin];
+// The 11 window weights travel as a by-value kernel argument (constant bank of the launch): no per-device symbol to
+// initialise, nothing to copy during a CUDA-graph capture, safe from any thread.
+struct GaussWin { float w[kWin]; };
 
 // Forward: per pixel/channel SSIM map terms; writes the three partial-derivative maps needed by the
 // backward (dS/dmu1, dS/dE[x^2], dS/dE[xy]) and accumulates sum(ssim) and sum|x-y| into sums[0..1].
 __global__ void __launch_bounds__(kTW * kTH)
 ssim_l1_forward_kernel(const float* __restrict__ x, const float* __restrict__ y, int C, int H, int W,
                        float* __restrict__ dmu, float* __restrict__ de11, float* __restrict__ de12,
-                       double* __restrict__ sums) {
+                       double* __restrict__ sums, const GaussWin win) {
     __shared__ float sx[kPH][kPW], sy[kPH][kPW];
     __shared__ float h[5][kPH][kTW];     // horizontally filtered x, y, xx, yy, xy
     __shared__ float red[2][kTW * kTH / 32];
@@ -62,7 +85,7 @@ ssim_l1_forward_kernel(const float* __restrict__ x, const float* __restrict__ y,
         float a = 0.f, b = 0.f, aa = 0.f, bb = 0.f, ab = 0.f;
 #pragma unroll
         for (int k = 0; k < kWin; ++k) {
-            const float w = c_gauss[k], xv = sx[r][q + k], yv = sy[r][q + k];
+            const float w = win.w[k], xv = sx[r][q + k], yv = sy[r][q + k];
             a = fmaf(w, xv, a); b = fmaf(w, yv, b);
             aa = fmaf(w, xv * xv, aa); bb = fmaf(w, yv * yv, bb); ab = fmaf(w, xv * yv, ab);
         }
@@ -75,7 +98,7 @@ ssim_l1_forward_kernel(const float* __restrict__ x, const float* __restrict__ y,
         float mu1 = 0.f, mu2 = 0.f, e11 = 0.f, e22 = 0.f, e12 = 0.f;
 #pragma unroll
         for (int k = 0; k < kWin; ++k) {
-            const float w = c_gauss[k];
+            const float w = win.w[k];
             mu1 = fmaf(w, h[0][threadIdx.y + k][threadIdx.x], mu1);
             mu2 = fmaf(w, h[1][threadIdx.y + k][threadIdx.x], mu2);
             e11 = fmaf(w, h[2][threadIdx.y + k][threadIdx.x], e11);
@@ -114,7 +137,8 @@ ssim_l1_forward_kernel(const float* __restrict__ x, const float* __restrict__ y,
 __global__ void __launch_bounds__(kTW * kTH)
 ssim_l1_backward_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ dmu,
                         const float* __restrict__ de11, const float* __restrict__ de12, int C, int H, int W,
-                        const float* __restrict__ grad_out, float w_ssim, float w_l1, float* __restrict__ gx) {
+                        const float* __restrict__ grad_out, float w_ssim, float w_l1, float* __restrict__ gx,
+                        const GaussWin win) {
     __shared__ float s[3][kPH][kPW];
     __shared__ float h[3][kPH][kTW];
     const int c = blockIdx.z, x0 = blockIdx.x * kTW, y0 = blockIdx.y * kTH;
@@ -134,7 +158,7 @@ ssim_l1_backward_kernel(const float* __restrict__ x, const float* __restrict__ y
         float a = 0.f, b = 0.f, d = 0.f;
 #pragma unroll
         for (int k = 0; k < kWin; ++k) {
-            const float w = c_gauss[k];
+            const float w = win.w[k];
             a = fmaf(w, s[0][r][q + k], a); b = fmaf(w, s[1][r][q + k], b); d = fmaf(w, s[2][r][q + k], d);
         }
         h[0][r][q] = a; h[1][r][q] = b; h[2][r][q] = d;
@@ -145,7 +169,7 @@ ssim_l1_backward_kernel(const float* __restrict__ x, const float* __restrict__ y
     float a = 0.f, b = 0.f, d = 0.f;
 #pragma unroll
     for (int k = 0; k < kWin; ++k) {
-        const float w = c_gauss[k];
+        const float w = win.w[k];
         a = fmaf(w, h[0][threadIdx.y + k][threadIdx.x], a);
         b = fmaf(w, h[1][threadIdx.y + k][threadIdx.x], b);
         d = fmaf(w, h[2][threadIdx.y + k][threadIdx.x], d);
@@ -225,7 +249,6 @@ masked_l1_backward_kernel(const float* __restrict__ depth_sil, const float* __re
     }
 }
 
-bool g_gauss_ready = false;
 
 }  // namespace
 
@@ -248,9 +271,36 @@ SB_API int sb_adam_step(float* params, const float* grads, float* exp_avg, float
     segs.n = num_segments;
     for (int k = 0; k < num_segments; ++k) { segs.end[k] = seg_end[k]; segs.lr[k] = (float)(-(seg_lr[k] / bc1)); }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(params, grads, exp_avg, exp_avg_sq, n, segs,
-                                                              (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2),
-                                                              (float)eps, (float)sqrt(bc2));
+    adam_kernel<false><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(params, grads, exp_avg, exp_avg_sq, n, segs,
+                                                                     (float)(1.0 - beta1), (float)beta2,
+                                                                     (float)(1.0 - beta2), (float)eps, (float)sqrt(bc2),
+                                                                     nullptr, nullptr);
+    SB_LAUNCH_CHECK("adam_kernel");
+    return SB_OK;
+}
+
+SB_API size_t sb_adam_clock_bytes(void) { return sizeof(AdamClock); }
+
+SB_API int sb_adam_step_guarded(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, size_t n,
+                                const uint32_t* seg_end, const double* seg_lr, int num_segments, void* clock_dev,
+                                const float* skip_if_nonzero, double beta1, double beta2, double eps, void* stream) {
+    if (!params || !grads || !exp_avg || !exp_avg_sq || !seg_end || !seg_lr || !clock_dev || num_segments < 1 ||
+        num_segments > kMaxSeg)
+        return SB_ERR_BAD_ARG;
+    if (n == 0) return SB_OK;
+    AdamSegs segs;
+    segs.n = num_segments;
+    AdamLrs lrs;
+    lrs.n = num_segments;
+    for (int k = 0; k < num_segments; ++k) { segs.end[k] = seg_end[k]; segs.lr[k] = 0.f; lrs.lr[k] = seg_lr[k]; }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    AdamClock* clk = static_cast<AdamClock*>(clock_dev);
+    adam_clock_kernel<<<1, 1, 0, st>>>(clk, skip_if_nonzero, lrs, beta1, beta2);
+    SB_LAUNCH_CHECK("adam_clock_kernel");
+    adam_kernel<true><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(params, grads, exp_avg, exp_avg_sq, n, segs,
+                                                                    (float)(1.0 - beta1), (float)beta2,
+                                                                    (float)(1.0 - beta2), (float)eps, 0.f, clk,
+                                                                    skip_if_nonzero);
     SB_LAUNCH_CHECK("adam_kernel");
     return SB_OK;
 }
@@ -281,17 +331,14 @@ SB_API int sb_masked_l1_backward(const float* depth_sil, const float* gt_depth, 
     return SB_OK;
 }
 
-static int ensure_gauss() {
-    if (g_gauss_ready) return SB_OK;
-    float g[kWin]; double sum = 0.0;
-    for (int i = 0; i < kWin; ++i) { g[i] = (float)exp(-(double)((i - kWin / 2) * (i - kWin / 2)) / (2.0 * 1.5 * 1.5)); sum += g[i]; }
-    // slam_external.gaussian(): float32 exp values divided by their float32 sum
-    float fs = 0.f; for (int i = 0; i < kWin; ++i) fs += g[i];
-    for (int i = 0; i < kWin; ++i) g[i] = g[i] / fs;
-    (void)sum;
-    SB_CUDA_CHECK(cudaMemcpyToSymbol(c_gauss, g, sizeof(g)));
-    g_gauss_ready = true;
-    return SB_OK;
+// slam_external.gaussian(): float32 exp values divided by their float32 sum (R/utils/slam_external.py:54-57)
+static GaussWin gauss_window() {
+    GaussWin g;
+    for (int i = 0; i < kWin; ++i) g.w[i] = (float)exp(-(double)((i - kWin / 2) * (i - kWin / 2)) / (2.0 * 1.5 * 1.5));
+    float fs = 0.f;
+    for (int i = 0; i < kWin; ++i) fs += g.w[i];
+    for (int i = 0; i < kWin; ++i) g.w[i] = g.w[i] / fs;
+    return g;
 }
 
 SB_API size_t sb_image_loss_workspace_floats(int C, int H, int W) { return (size_t)3 * C * H * W; }
@@ -301,13 +348,11 @@ SB_API size_t sb_image_loss_workspace_floats(int C, int H, int W) { return (size
 SB_API int sb_image_loss_forward(const float* x, const float* y, int C, int H, int W, float* work, double* sums,
                                  void* stream) {
     if (!x || !y || !work || !sums || C < 1 || H < 1 || W < 1) return SB_ERR_BAD_ARG;
-    int rc = ensure_gauss();
-    if (rc != SB_OK) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     SB_CUDA_CHECK(cudaMemsetAsync(sums, 0, 2 * sizeof(double), st));
     const size_t n = (size_t)C * H * W;
     dim3 grid((W + kTW - 1) / kTW, (H + kTH - 1) / kTH, C), block(kTW, kTH);
-    ssim_l1_forward_kernel<<<grid, block, 0, st>>>(x, y, C, H, W, work, work + n, work + 2 * n, sums);
+    ssim_l1_forward_kernel<<<grid, block, 0, st>>>(x, y, C, H, W, work, work + n, work + 2 * n, sums, gauss_window());
     SB_LAUNCH_CHECK("ssim_l1_forward_kernel");
     return SB_OK;
 }
@@ -315,12 +360,10 @@ SB_API int sb_image_loss_forward(const float* x, const float* y, int C, int H, i
 SB_API int sb_image_loss_backward(const float* x, const float* y, int C, int H, int W, const float* work,
                                   const float* grad_out, float w_ssim, float w_l1, float* grad_x, void* stream) {
     if (!x || !y || !work || !grad_out || !grad_x || C < 1 || H < 1 || W < 1) return SB_ERR_BAD_ARG;
-    int rc = ensure_gauss();
-    if (rc != SB_OK) return rc;
     const size_t n = (size_t)C * H * W;
     dim3 grid((W + kTW - 1) / kTW, (H + kTH - 1) / kTH, C), block(kTW, kTH);
     ssim_l1_backward_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
-        x, y, work, work + n, work + 2 * n, C, H, W, grad_out, w_ssim, w_l1, grad_x);
+        x, y, work, work + n, work + 2 * n, C, H, W, grad_out, w_ssim, w_l1, grad_x, gauss_window());
     SB_LAUNCH_CHECK("ssim_l1_backward_kernel");
     return SB_OK;
 }

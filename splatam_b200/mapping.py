@@ -286,12 +286,14 @@ class FlatGaussians:
         n = sum(math.prod(s) for s in self.shapes.values())
         dev = tensors["means3D"].device
         self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
-        # ONE all-reduce bucket: [per-Gaussian gradients (n) | per-Gaussian "seen" flags as 0/1 floats (P) | loss (1)]
+        # ONE all-reduce bucket: [per-Gaussian gradients (n) | per-Gaussian "seen" flags as 0/1 floats (P) | loss (1) |
+        # capacity-overflow flag of the sync-free rasterizer (1): non-zero on ANY rank => every rank skips the update]
         P_ = tensors["means3D"].shape[0]
-        self.bucket = torch.zeros(n + P_ + 1, dtype=torch.float32, device=dev)
+        self.bucket = torch.zeros(n + P_ + 2, dtype=torch.float32, device=dev)
         self.flat_grad = self.bucket[:n]
         self.seen_f = self.bucket[n:n + P_]
-        self.loss_slot = self.bucket[n + P_:]
+        self.loss_slot = self.bucket[n + P_:n + P_ + 1]
+        self.overflow_slot = self.bucket[n + P_ + 1:]
         self.params, off = {}, 0
         for k in GAUSSIAN_KEYS:
             m = math.prod(self.shapes[k])
@@ -404,7 +406,7 @@ class ShardedMapper:
             flat = map_ops.compact_flat(self.g.flat, P, w, m8, dst, P_new)
             m = map_ops.compact_flat(self.opt.m, P, w, m8, dst, P_new)
             v = map_ops.compact_flat(self.opt.v, P, w, m8, dst, P_new)
-            self._rebuild(flat, P_new, m, v, self.opt.t)
+            self._rebuild(flat, P_new, m, v, self.opt.applied_steps()[0])
             return P_new
         P_new = int(keep.sum())
         if P_new == P:
@@ -467,7 +469,7 @@ class ShardedMapper:
                     parts += [buf[off:off + w * P], torch.zeros(w * n_new, device=dev)]
                     off += w * P
                 return torch.cat(parts)
-            self._rebuild(flat, P + n_new, grown(self.opt.m), grown(self.opt.v), self.opt.t)
+            self._rebuild(flat, P + n_new, grown(self.opt.m), grown(self.opt.v), self.opt.applied_steps()[0])
         else:
             state = {}
             for k in GAUSSIAN_KEYS:
@@ -499,22 +501,34 @@ class ShardedMapper:
         return n
 
     # ---- CUDA-graph mode -----------------------------------------------------------------------------------
-    def enable_graph(self, window, slack=1.3):
+    def enable_graph(self, window, slack=1.3, capacity=None):
         """Capture loss forward + backward of one keyframe into a CUDA graph (sync-free rasterizer with a fixed
-        instance capacity = slack x the largest num_rendered over `window`).  Afterwards `step` copies the chosen
-        keyframe into static buffers and replays the graph: ~6 launches per step instead of ~60, and no host
-        synchronisation, so the step no longer depends on host speed.  Frames must share one camera."""
+        instance capacity = slack x the largest num_rendered over `window`, or `capacity`).  Afterwards `step`
+        copies the chosen keyframe into static buffers and replays the graph: ~6 launches per step instead of ~60,
+        and no host synchronisation, so the step no longer depends on host speed.  Frames must share one camera.
+
+        Safety: if the map moves or grows until a render needs more instances than the capacity, the rasterizer
+        raises its device-side overflow flag and writes NaN images; the flag travels in the all-reduce bucket, the
+        guarded Adam step (device-side step clock) is a no-op on every rank for that step, and `step` -- which
+        polls the flag with a one-step lag, never blocking on the step in flight -- re-captures with a larger
+        capacity.  An overflowed step therefore costs time, never correctness."""
         assert self.fused and self.g.flat.is_cuda and self.render is default_render
         from .rasterizer import GaussianRasterizer
         dev = self.g.flat.device
         f0 = window[0]
-        worst = 0
-        for fr in window:            # one synchronous pass to size the capacity
-            with torch.no_grad():
-                rgb, dep = fused_rendervars(self.params(), fr["id"], fr["w2c"], camera_grad=False)
-                c, _, _ = GaussianRasterizer(fr["cam"])(**rgb)
-            worst = max(worst, _last_num_rendered())
-        self._cap = int(worst * slack) + 4096
+        if capacity is None:
+            worst = 0
+            for fr in window:            # one synchronous pass to size the capacity
+                with torch.no_grad():
+                    rgb, dep = fused_rendervars(self.params(), fr["id"], fr["w2c"], camera_grad=False)
+                    c, _, _ = GaussianRasterizer(fr["cam"])(**rgb)
+                worst = max(worst, _last_num_rendered())
+            capacity = int(worst * slack) + 4096
+        self._cap = int(capacity)
+        self._slack = slack
+        self._polls = []                 # (event, pinned copy of the overflow slot) of steps in flight
+        self.overflow_events = getattr(self, "overflow_events", 0)
+        self._pin = [torch.empty(1, dtype=torch.float32, pin_memory=True) for _ in range(8)]
         self._static = dict(id=f0["id"], cam=f0["cam"], w2c=f0["w2c"].clone(), im=f0["im"].clone(), depth=f0["depth"].clone(),
                             pose=tuple(t.clone() for t in pose_matrices(self.params(), f0["id"])))
         side = torch.cuda.Stream(dev)
@@ -532,6 +546,7 @@ class ShardedMapper:
             loss.backward()
             self.g.seen_f.copy_(radius > 0)
             self.g.loss_slot.copy_(loss.detach().reshape(1))
+            self.g.overflow_slot.copy_(GaussianRasterizer.last_state(dev).header()[2:3])     # int32 0/1 -> float
         return self._cap
 
     def _replay(self, frame):
@@ -545,9 +560,29 @@ class ShardedMapper:
         self._graph.replay()
 
     def check_capacity(self):
-        """(num_rendered, overflowed) of the last graph replay; synchronises.  Call occasionally."""
+        """(num_rendered, overflowed) of the last graph replay; synchronises."""
         from .rasterizer import GaussianRasterizer
-        return GaussianRasterizer.last_counts()
+        return GaussianRasterizer.last_counts(self.g.flat.device)
+
+    def effective_steps(self):
+        """(Adam steps applied, steps skipped because a render overflowed the instance capacity); synchronises."""
+        return self.opt.applied_steps() if self.fused else (self.step_idx, 0)
+
+    def _poll_overflow(self, window, block=False):
+        """Looks at the overflow flags of COMPLETED earlier steps (one-step lag: never waits for the step in flight
+        unless `block`); on overflow grows the capacity from the measured instance count and re-captures."""
+        hit = False
+        while self._polls and (block or len(self._polls) > 1 or self._polls[0][0].query()):
+            ev, host = self._polls.pop(0)
+            ev.synchronize()
+            hit = hit or float(host[0]) != 0.0
+        if hit:
+            torch.cuda.synchronize(self.g.flat.device)
+            self._polls = []
+            n_r, _ = self.check_capacity()
+            self.overflow_events += 1
+            self.enable_graph(window, slack=self._slack, capacity=max(int(n_r * self._slack), int(self._cap * 1.5)) + 4096)
+        return hit
 
     def schedule(self, window_size):
         """Keyframe index (into the window) rendered by each rank this step: a shared-seed permutation
@@ -566,6 +601,7 @@ class ShardedMapper:
         picks = self.schedule(len(window))
         graphed = getattr(self, "_graph", None) is not None
         if graphed:
+            self._poll_overflow(window)
             self._replay(window[picks[self.rank]])
         else:
             self.g.zero_grad()
@@ -575,7 +611,15 @@ class ShardedMapper:
         if self.dist and self.world > 1:
             # ONE collective per step: gradients, seen flags (sum of 0/1 > 0 == OR) and the loss travel together
             self.dist.all_reduce(self.g.bucket, op=self.dist.ReduceOp.SUM, group=self.group)
-        self.opt.step()
+        if graphed:
+            self.opt.step_guarded(self.g.overflow_slot)        # no-op on every rank if any rank's render overflowed
+            host = self._pin[self.step_idx % len(self._pin)]
+            host.copy_(self.g.overflow_slot, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            self._polls.append((ev, host))
+        else:
+            self.opt.step()
         self.step_idx += 1
         seen = self.g.seen_f > 0
         loss = self.g.loss_slot[0] / self.world

@@ -82,7 +82,7 @@ def _settings_pack(rs, device):
 
 _SIZE_CACHE = {}
 _R_HINT = {}
-_LAST_ASYNC_STATE = [None]
+_LAST_ASYNC_STATE = {}      # device index -> state of the most recent sync-free forward on that device
 _LAST_SYNC_R = [0]          # num_rendered of the most recent synchronous forward
 
 
@@ -129,6 +129,10 @@ class _State:
     """Scratch kept alive between forward and backward (the reference saves its three byte buffers
     on the autograd ctx, __init__.py:82-84)."""
     __slots__ = ("geom", "binning", "image", "num_rendered", "settings", "P")
+
+    def header(self):
+        """int32 view [num_rendered, num_visible, overflow flag] of the device-side counters (no synchronisation)."""
+        return self.geom[:12].view(torch.int32)
 
     def counts(self):
         """(num_rendered, overflowed) of a sync-free forward; synchronises the current stream."""
@@ -186,7 +190,7 @@ def _forward_impl(means3D, colors_precomp, opacities, scales, rotations, cov3Ds_
                 state.geom.numel(), state.binning.data_ptr(), state.binning.numel(), capacity, state.image.data_ptr(),
                 state.image.numel(), color.data_ptr(), _ptr(color2), depth.data_ptr(), st), "sb_forward_async")
             state.num_rendered = capacity
-            _LAST_ASYNC_STATE[0] = state
+            _LAST_ASYNC_STATE[device.index] = state
             saved = (means3D, colors_precomp, scales, rotations, cov3Ds_precomp)
             if sets == 2:
                 return color, color2, radii, depth, state, saved + (colors2,)
@@ -206,7 +210,7 @@ def _forward_impl(means3D, colors_precomp, opacities, scales, rotations, cov3Ds_
                             _ptr(cov3Ds_precomp), _ptr(colors_precomp), _ptr(colors2), _ptr(radii),
                             state.geom.data_ptr(), state.geom.numel(), bin_ptr, bin_bytes, state.image.data_ptr(),
                             state.image.numel(), color.data_ptr(), _ptr(color2), depth.data_ptr(), ctypes.byref(R), st)
-        if rc == 2:      # SB_ERR_WORKSPACE: stage 1 is done, the guess was too small -> size exactly and finish
+        if rc == 5:      # SB_ERR_BINNING_TOO_SMALL: stage 1 is done, the guess was too small -> size exactly and finish
             _lib.check(lib.sb_binning_workspace_bytes_ex(R.value, W, H, sets, ctypes.byref(n)),
                        "sb_binning_workspace_bytes_ex")
             state.binning = _ws(n.value, device)
@@ -381,9 +385,16 @@ class GaussianRasterizer(nn.Module):
         self.max_rendered = max_rendered
 
     @staticmethod
-    def last_counts():
-        """(num_rendered, overflowed) of the most recent sync-free forward of this process; synchronises."""
-        st = _LAST_ASYNC_STATE[0]
+    def last_state(device=None):
+        """Workspace state of the most recent sync-free forward on `device` (default: the current device)."""
+        idx = torch.cuda.current_device() if device is None else torch.device(device).index
+        return _LAST_ASYNC_STATE.get(idx)
+
+    @staticmethod
+    def last_counts(device=None):
+        """(num_rendered, overflowed) of the most recent sync-free forward on `device` (default: the current
+        device); synchronises.  On overflow the images of that forward are NaN."""
+        st = GaussianRasterizer.last_state(device)
         return None if st is None else st.counts()
 
     def markVisible(self, positions):

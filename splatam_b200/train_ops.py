@@ -33,8 +33,39 @@ class FusedAdam:
         self.seg_end = (ctypes.c_uint32 * self.n)(*ends)
         self.seg_lr = (ctypes.c_double * self.n)(*[float(x) for x in seg_lrs])
         self.betas, self.eps, self.t = betas, eps, int(step)
+        self.clock = None           # device-side step clock of the guarded mode (created on first use)
+
+    def _clock(self):
+        if self.clock is None:
+            lib = _lib.load()
+            nints = (int(lib.sb_adam_clock_bytes()) + 3) // 4
+            self.clock = torch.zeros(nints, dtype=torch.int32, device=self.flat.device)
+            self.clock[0] = self.t
+        return self.clock
+
+    def step_guarded(self, skip_if_nonzero=None):
+        """One Adam step whose step count lives on the device; a no-op (count unchanged) when the device float
+        `skip_if_nonzero[0]` is non-zero.  Never synchronises.  `applied_steps()` reads the clock back."""
+        lib = _lib.load()
+        clk = self._clock()
+        with torch.cuda.device(self.flat.device):
+            _lib.check(lib.sb_adam_step_guarded(
+                self.flat.data_ptr(), self.flat_grad.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), self.flat.numel(),
+                self.seg_end, self.seg_lr, self.n, clk.data_ptr(),
+                None if skip_if_nonzero is None else skip_if_nonzero.data_ptr(), self.betas[0], self.betas[1], self.eps,
+                _stream(self.flat.device)), "sb_adam_step_guarded")
+
+    def applied_steps(self):
+        """(steps applied, steps skipped) of the guarded mode; synchronises."""
+        if self.clock is None:
+            return self.t, 0
+        c = self.clock[:2].tolist()
+        self.t = int(c[0])
+        return int(c[0]), int(c[1])
 
     def step(self):
+        if self.clock is not None:      # once guarded, the device clock is the step count
+            return self.step_guarded(None)
         self.t += 1
         lib = _lib.load()
         with torch.cuda.device(self.flat.device):

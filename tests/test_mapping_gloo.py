@@ -125,7 +125,7 @@ def test_prune_and_grow_keep_replicas_identical():
     [p.join(60) for p in procs]
     (_, P1a, P2a, nb_a, flat_a, la), (_, P1b, P2b, nb_b, flat_b, lb) = res
     assert P1a == P1b and 0 < P1a < 96 and P2a == P2b == P1a + 7
-    assert nb_a == nb_b == P2a * 12 + P2a + 1                         # gradients | seen flags | loss
+    assert nb_a == nb_b == P2a * 12 + P2a + 2                         # gradients | seen flags | loss | overflow flag
     assert (flat_a == flat_b).all() and abs(la - lb) < 1e-7
 
 
