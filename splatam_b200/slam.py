@@ -134,6 +134,31 @@ def run_slam(gauss_init, frames, cam, render=None, tracking_iters=20, mapping_it
     return dict(rots=rots, trans=trans, psnr=sum(vals) / len(vals), gauss=final, counts=counts)
 
 
+def w2c_list(rots, trans):
+    """Per-frame 4x4 w2c matrices from the packed pose tensors (R/utils/eval_helpers.py:555-563)."""
+    return [_curr_w2c(rots, trans, t) for t in range(rots.shape[-1])]
+
+
+def ate_horn(gt_w2c, est_w2c):
+    """The reference's trajectory metric, restated: evaluate_ate + align (R/utils/eval_helpers.py:23-77): the
+    translation columns of the w2c matrices are aligned rigidly with Horn's closed form (SVD of the 3x3
+    cross-covariance, reflection fix on the last singular direction) and the MEAN residual norm is returned -- the
+    number the reference prints as "Final Average ATE RMSE" (:569-570)."""
+    import numpy as np
+    model = np.stack([m[:3, 3].detach().cpu().double().numpy() for m in gt_w2c], 1)       # 3 x n (gt)
+    data = np.stack([m[:3, 3].detach().cpu().double().numpy() for m in est_w2c], 1)       # 3 x n (estimate)
+    mz, dz = model - model.mean(1, keepdims=True), data - data.mean(1, keepdims=True)
+    W = mz @ dz.T                                   # sum of outer(model_i, data_i)
+    U, _, Vh = np.linalg.svd(W.T)
+    S = np.eye(3)
+    if np.linalg.det(U) * np.linalg.det(Vh) < 0:
+        S[2, 2] = -1.0
+    rot = U @ S @ Vh
+    t = data.mean(1, keepdims=True) - rot @ model.mean(1, keepdims=True)
+    err = rot @ model + t - data
+    return float(np.sqrt((err * err).sum(0)).mean())
+
+
 def ate_rmse(rots_est, trans_est, rots_gt, trans_gt):
     """RMSE of camera-centre positions (all poses share frame 0, so no alignment is needed)."""
     def centres(rots, trans):

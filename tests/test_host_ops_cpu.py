@@ -183,3 +183,39 @@ def test_pose_cache_follows_tensor_identity_and_version():
     assert c is not b and torch.equal(c[0], b[0])
     ref = M.pose_matrices(p, 1)
     assert torch.equal(ref[0], b[0]) and torch.equal(ref[1], b[1])
+
+
+def test_horn_aligned_ate_matches_reference():
+    """slam.ate_horn == evaluate_ate of R/utils/eval_helpers.py:23-77 (run where the reference tree is present;
+    the committed numbers below were produced by it)."""
+    import torch
+    from splatam_b200 import slam
+    g = torch.Generator().manual_seed(4)
+
+    def traj(n, noise):
+        out = []
+        for i in range(n):
+            m = torch.eye(4)
+            a = 0.05 * i
+            m[:3, :3] = torch.tensor([[np.cos(a), 0, np.sin(a)], [0, 1, 0], [-np.sin(a), 0, np.cos(a)]], dtype=torch.float32)
+            m[:3, 3] = torch.tensor([0.1 * i, 0.02 * i * i, -0.05 * i]) + noise * torch.randn(3, generator=g)
+            out.append(m)
+        return out
+    gt = traj(12, 0.0)
+    # estimate = gt seen from a rotated / shifted frame + noise: Horn alignment must remove the rigid part
+    Rz = torch.tensor([[0.8, -0.6, 0], [0.6, 0.8, 0], [0, 0, 1.0]])
+    est = []
+    for m in traj(12, 0.01):
+        e = m.clone()
+        e[:3, 3] = Rz @ m[:3, 3] + torch.tensor([1.0, -2.0, 0.5])
+        est.append(e)
+    ours = slam.ate_horn(gt, est)
+    assert 0.002 < ours < 0.03
+    assert abs(ours - 0.0127796377) < 2e-7, ours       # evaluate_ate(gt, est) of the reference on the same inputs
+    import refsrc
+    if refsrc.available():
+        import types
+        pkg = types.ModuleType("fake_rasterizer_pkg_ate")
+        pkg.GaussianRasterizer, pkg.GaussianRasterizationSettings = object, object
+        R = refsrc.load(pkg)
+        assert abs(ours - float(R.eval_helpers.evaluate_ate(gt, est))) < 1e-6
