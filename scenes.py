@@ -155,7 +155,7 @@ def _surface_depth(u, v):
     return 2.5 + 0.8 * torch.sin(u / 130.0) * torch.cos(v / 90.0) + 0.3 * torch.sin(u / 23.0 + v / 31.0)
 
 
-def view_filling(seed=12, cam=REPLICA, P=None, stride=1, anisotropic=False, w2c=None, opacity=(0.45, 0.6)):
+def view_filling(seed=12, cam=REPLICA, P=None, stride=1, anisotropic=False, w2c=None, opacity=(0.45, 0.6), margin=0):
     """A map that FILLS the view the way SplaTAM's maps do: one Gaussian per pixel of the first frame,
     back-projected through the depth map, sigma_world = depth / f (one pixel std on screen), logit opacity ~ 0
     (R/scripts/splatam.py:67-118,120-157,196-203: get_pointcloud + initialize_params with the "projective"
@@ -165,8 +165,9 @@ def view_filling(seed=12, cam=REPLICA, P=None, stride=1, anisotropic=False, w2c=
     hundreds of entries long -- unlike `room`, where ~97 % of the Gaussians lie outside the frustum."""
     g = torch.Generator().manual_seed(seed)
     w, h, fx, fy, cx, cy = cam["w"], cam["h"], cam["fx"], cam["fy"], cam["cx"], cam["cy"]
-    vv, uu = torch.meshgrid(torch.arange(0, h, stride, dtype=torch.float32), torch.arange(0, w, stride, dtype=torch.float32),
-                            indexing="ij")
+    # margin > 0 extends the surface beyond the image borders (pixels), so a moving camera keeps seeing a covered view
+    vv, uu = torch.meshgrid(torch.arange(-margin, h + margin, stride, dtype=torch.float32),
+                            torch.arange(-margin, w + margin, stride, dtype=torch.float32), indexing="ij")
     u, v = uu.reshape(-1), vv.reshape(-1)
     n_grid = u.numel()
     P = n_grid if P is None else int(P)
@@ -176,8 +177,8 @@ def view_filling(seed=12, cam=REPLICA, P=None, stride=1, anisotropic=False, w2c=
         size = torch.ones(P)
     else:
         extra = P - n_grid
-        u = torch.cat([u, w * _rand(g, extra)])
-        v = torch.cat([v, h * _rand(g, extra)])
+        u = torch.cat([u, -margin + (w + 2 * margin) * _rand(g, extra)])
+        v = torch.cat([v, -margin + (h + 2 * margin) * _rand(g, extra)])
         size = torch.cat([torch.ones(n_grid), 0.8 + 0.5 * _rand(g, extra)])
     z = _surface_depth(u, v) * (1.0 + 0.004 * torch.randn(P, generator=g))
     means = torch.stack([(u - cx) * z / fx, (v - cy) * z / fy, z], 1)

@@ -264,11 +264,13 @@ def track_frame(params, frame, render=None, num_iters=40, lr_rot=0.0004, lr_tran
         opt.zero_grad(set_to_none=True)
         loss, _ = tracking_loss(params, frame, render, fused=fused)
         loss.backward()
+        opt.step()
         with torch.no_grad():
+            # as the reference (splatam.py:703-712): the candidate is the pose AFTER the step, ranked by the loss that
+            # was evaluated before it
             lv = float(loss)
             if best is None or lv < best:
                 best, best_rot, best_tran = lv, rots[..., t].detach().clone(), trans[..., t].detach().clone()
-        opt.step()
         losses.append(lv)
     with torch.no_grad():
         rots[..., t] = best_rot
@@ -583,6 +585,26 @@ class ShardedMapper:
             self.overflow_events += 1
             self.enable_graph(window, slack=self._slack, capacity=max(int(n_r * self._slack), int(self._cap * 1.5)) + 4096)
         return hit
+
+    def timing_breakdown(self, window, reps=10):
+        """Device time (CUDA events, ms) of the step's collective alone -- the all-reduce of the packed bucket -- measured
+        outside any timed benchmark region; {} on a single rank."""
+        if not (self.dist and self.world > 1):
+            return {}
+        dev = self.g.flat.device
+        buf = torch.zeros_like(self.g.bucket)
+        for _ in range(3):
+            self.dist.all_reduce(buf, op=self.dist.ReduceOp.SUM, group=self.group)
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            self.dist.all_reduce(buf, op=self.dist.ReduceOp.SUM, group=self.group)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = torch.tensor([e0.elapsed_time(e1) / reps], device=dev)
+        self.dist.all_reduce(ms, op=self.dist.ReduceOp.MAX, group=self.group)
+        return {"allreduce_ms": float(ms.item()), "allreduce_algbw_gbs": buf.numel() * 4 / (float(ms.item()) * 1e-3) / 1e9}
 
     def schedule(self, window_size):
         """Keyframe index (into the window) rendered by each rank this step: a shared-seed permutation

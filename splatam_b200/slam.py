@@ -64,7 +64,8 @@ def _curr_w2c(rots, trans, t):
 
 def run_slam(gauss_init, frames, cam, render=None, tracking_iters=20, mapping_iters=8, keyframe_every=2,
              window=4, fused=None, seed=0, intrinsics=None, add_new_gaussians=False, sil_thres=0.5, prune_dict=None,
-             scene_radius=None, select_keyframes=False, checkpoint_dir=None, first_frame_iters=0):
+             scene_radius=None, select_keyframes=False, checkpoint_dir=None, first_frame_iters=0, map_every=None,
+             graph=False, timing=None):
     """Tracks every frame and maps on keyframes.  gauss_init: dict of the five Gaussian tensors (the map's
     starting point); frames: list of dict(id, cam, w2c, im, depth).  Returns dict(rots, trans, psnr, gauss).
 
@@ -73,7 +74,15 @@ def run_slam(gauss_init, frames, cam, render=None, tracking_iters=20, mapping_it
     iterations (prune_gaussians' schedule keys), `select_keyframes` picks the mapping window by re-projection
     overlap (window-2 selected + the last keyframe + the current frame) instead of the last `window` keyframes,
     `checkpoint_dir` writes params<t>.npz per mapped frame and params.npz at the end; `first_frame_iters` mapping
-    iterations run on frame 0 before tracking starts (needed when the map is a raw back-projection)."""
+    iterations run on frame 0 before tracking starts (needed when the map is a raw back-projection).
+    `map_every` (default: keyframe_every) maps every map_every-th frame while only every keyframe_every-th frame joins
+    the keyframe list, as the reference's two config keys do (splatam.py:777,912).  `graph`: each mapping phase is
+    captured into a CUDA graph over the sync-free rasterizer (fused path only).  `timing`: dict that receives the
+    accumulated wall seconds of tracking / mapping (synchronised) and the mapping iteration count."""
+    import time
+    map_every = keyframe_every if map_every is None else map_every
+    timing = {} if timing is None else timing
+    timing.update(tracking_s=0.0, mapping_s=0.0, mapping_iters=0, tracking_iters=0)
     dev = gauss_init["means3D"].device
     T = len(frames)
     rots = torch.zeros(1, 4, T, device=dev); rots[:, 0] = 1.0
@@ -96,29 +105,47 @@ def run_slam(gauss_init, frames, cam, render=None, tracking_iters=20, mapping_it
                 rots[0, :, t] = rots[0, :, t - 1]
                 trans[0, :, t] = trans[0, :, t - 1]
         params = dict({k: v.detach() for k, v in mapper.g.params.items()}, cam_unnorm_rots=rots, cam_trans=trans)
+        torch.cuda.synchronize(dev) if dev.type == "cuda" else None
+        t0 = time.perf_counter()
         M.track_frame(params, frames[t], render=render, num_iters=tracking_iters, fused=fused)
+        torch.cuda.synchronize(dev) if dev.type == "cuda" else None
+        timing["tracking_s"] += time.perf_counter() - t0
+        timing["tracking_iters"] += tracking_iters
         rots, trans = params["cam_unnorm_rots"].detach(), params["cam_trans"].detach()
         mapper.cam = dict(cam_unnorm_rots=rots, cam_trans=trans)
         cam_now = mapper.sync_camera()            # multi-rank runs: rank 0's tracking result is the pose of record
         rots, trans = cam_now["cam_unnorm_rots"], cam_now["cam_trans"]
-        if t % keyframe_every == 0:
-            cur = dict(frames[t], est_w2c=_curr_w2c(rots, trans, t))
+        cur = dict(frames[t], est_w2c=_curr_w2c(rots, trans, t))
+        if t % map_every == 0:
             if add_new_gaussians:
                 mapper.add_new_gaussians(frames[t], t, intrinsics, sil_thres)
             if select_keyframes:
                 from .keyframes import keyframe_selection_overlap
+                if mapper.world > 1:      # the selection draws from the global RNGs: every rank must draw the same
+                    import numpy as _np
+                    torch.manual_seed(1000 * seed + t); _np.random.seed(1000 * seed + t)
                 sel = keyframe_selection_overlap(frames[t]["depth"], cur["est_w2c"], torch.as_tensor(intrinsics).to(dev),
                                                  keyframes[:-1], max(window - 2, 0))
                 win = [keyframes[int(i)] for i in sel] + [keyframes[-1], cur]
             else:
                 win = (keyframes + [cur])[-window:]
             mapper.reset_optimizer()                          # splatam.py:822
+            if graph:
+                mapper.enable_graph(win)
+            torch.cuda.synchronize(dev) if dev.type == "cuda" else None
+            t0 = time.perf_counter()
             for it in range(mapping_iters):
                 mapper.step(win)
                 if prune_dict is not None:
                     mapper.prune_gaussians(it, prune_dict, scene_radius)
-            keyframes.append(cur)
+            if graph and getattr(mapper, "_graph", None) is not None:
+                mapper._poll_overflow(win, block=True)
+            torch.cuda.synchronize(dev) if dev.type == "cuda" else None
+            timing["mapping_s"] += time.perf_counter() - t0
+            timing["mapping_iters"] += mapping_iters
             counts.append(mapper.g.shapes["means3D"][0])
+        if t % keyframe_every == 0:
+            keyframes.append(cur)
             if checkpoint_dir is not None:
                 from . import formats
                 formats.save_params_ckpt(dict(mapper.g.params, cam_unnorm_rots=rots, cam_trans=trans), checkpoint_dir, t)
