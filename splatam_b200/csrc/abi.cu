@@ -1,6 +1,7 @@
 // abi.cu -- the extern "C" boundary declared in include/splatam_b200.h: argument checks, workspace
 // carving, stage sequencing.  No torch, no STL types in any signature.
 #include "common.cuh"
+#include "radix_sort.cuh"
 #include <string.h>
 #include <stdio.h>
 #include <vector>
@@ -37,12 +38,13 @@ GeometryWs carve_geometry(void* ws, int P, size_t* total) {
     g.geomA = c.take<float4>(n);
     g.geomB = c.take<float4>(n);
     g.rect = c.take<uint2>(n);
-    g.iota = c.take<uint32_t>(n);
     g.sorted_key = c.take<uint32_t>(n);
     g.sorted_idx = c.take<uint32_t>(n);
     g.offsets = c.take<uint32_t>(n);
-    g.cub_temp_bytes = geometry_cub_temp_bytes((int)n);
-    g.cub_temp = c.take<char>(g.cub_temp_bytes);
+    g.sort_temp_bytes = radix_temp_bytes((int)n, 32);
+    g.sort_temp = c.take<char>(g.sort_temp_bytes);
+    g.scan_temp_bytes = geometry_scan_temp_bytes((int)n);
+    g.scan_temp = c.take<char>(g.scan_temp_bytes);
     if (total) *total = c.used();
     return g;
 }
@@ -51,16 +53,15 @@ BinningWs carve_binning(void* ws, int R, int tiles, int color_sets, size_t* tota
     Carver c(ws);
     BinningWs b;
     const size_t n = (size_t)(R > 0 ? R : 1);
-    const bool keys16 = higher_msb((uint32_t)tiles) <= 16 && tiles < 65535;
-    b.tile_unsorted = c.take<uint32_t>(keys16 ? (n + 1) / 2 : n);
+    b.tile_unsorted = c.take<uint32_t>(n);
     b.val_unsorted = c.take<uint32_t>(n);
-    b.tile_sorted = c.take<uint32_t>(keys16 ? (n + 1) / 2 : n);
+    b.tile_sorted = c.take<uint32_t>(n);
     b.point_list = c.take<uint32_t>(n);
     b.recA = c.take<float4>(n);
     b.recB = c.take<float4>(n);
     b.recC = c.take<float4>(n);
-    b.cub_temp_bytes = binning_cub_temp_bytes((int)n, keys16);
-    b.cub_temp = c.take<char>(b.cub_temp_bytes);
+    b.sort_temp_bytes = radix_temp_bytes((int)n, (int)higher_msb((uint32_t)tiles));
+    b.sort_temp = c.take<char>(b.sort_temp_bytes);
     b.recD = color_sets > 1 ? c.take<float4>(n) : nullptr;   // after everything else: the 1-set layout is a prefix
     if (total) *total = c.used();
     return b;
@@ -352,12 +353,8 @@ SB_API int sb_export_binning(const sb_settings* s, int P, int num_rendered, cons
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (num_rendered > 0 && (keys || point_list)) {
         const int R = num_rendered;
-        if (higher_msb((uint32_t)tiles) <= 16)
-            export_keys_kernel<uint16_t><<<(R + 255) / 256, 256, 0, st>>>(
-                R, reinterpret_cast<const uint16_t*>(b.tile_sorted), b.point_list, g.depth_key, keys, point_list);
-        else
-            export_keys_kernel<uint32_t><<<(R + 255) / 256, 256, 0, st>>>(R, b.tile_sorted, b.point_list,
-                                                                          g.depth_key, keys, point_list);
+        export_keys_kernel<uint32_t><<<(R + 255) / 256, 256, 0, st>>>(R, b.tile_sorted, b.point_list,
+                                                                      g.depth_key, keys, point_list);
         SB_LAUNCH_CHECK("export_keys_kernel");
     }
     const size_t hw = (size_t)s->image_width * s->image_height;

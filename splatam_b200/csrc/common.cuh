@@ -58,21 +58,22 @@ struct GeometryWs {
     float4*   geomA;         // [P]
     float4*   geomB;         // [P]
     uint2*    rect;          // [P]
-    uint32_t* iota;          // [P] 0..P-1 (sort payload in)
     uint32_t* sorted_key;    // [P] depth keys ascending
     uint32_t* sorted_idx;    // [P] Gaussian index in (depth, index) order
     uint32_t* offsets;       // [P] inclusive scan of tiles_touched in that order
-    void*     cub_temp;      // sort/scan scratch
-    size_t    cub_temp_bytes;
+    void*     sort_temp;     // radix_sort.cu scratch (histograms, look-back status, ping-pong pairs)
+    size_t    sort_temp_bytes;
+    void*     scan_temp;     // CUB inclusive-scan scratch
+    size_t    scan_temp_bytes;
 };
-size_t geometry_cub_temp_bytes(int P);
+size_t geometry_scan_temp_bytes(int P);
 GeometryWs carve_geometry(void* ws, int P, size_t* total);
 
 // ---- per-instance state (R = num_rendered tile instances) -------------------------------
 // Sorted SoA splat records staged by TMA into shared memory, 16 B each per array:
 // recA = geomA of the instance's Gaussian, recB = geomB, recC = {r, g, b, bits(index)}.
 struct BinningWs {
-    uint32_t* tile_unsorted; // [R] tile id per instance, (depth,index) order   (u16 or u32 view)
+    uint32_t* tile_unsorted; // [R] tile id per instance, (depth,index) order
     uint32_t* val_unsorted;  // [R] Gaussian index per instance
     uint32_t* tile_sorted;   // [R]
     uint32_t* point_list;    // [R] Gaussian index, (tile, depth, index) order == reference point_list
@@ -80,10 +81,9 @@ struct BinningWs {
     float4*   recB;          // [R]
     float4*   recC;          // [R]
     float4*   recD;          // [R] second colour set {e0, e1, e2, -} (fused two-set render only)
-    void*     cub_temp;
-    size_t    cub_temp_bytes;
+    void*     sort_temp;     // radix_sort.cu scratch
+    size_t    sort_temp_bytes;
 };
-size_t binning_cub_temp_bytes(int R, bool keys16);
 BinningWs carve_binning(void* ws, int R, int tiles, int color_sets, size_t* total);
 
 struct ImageWs {

@@ -9,7 +9,7 @@
 // written out with explicit __f*_rn intrinsics so this file's own contraction cannot change it).
 // Division, reciprocal and square root are IEEE correctly-rounded in both builds.
 #include "common.cuh"
-#include <cub/device/device_radix_sort.cuh>
+#include "radix_sort.cuh"
 #include <cub/device/device_scan.cuh>
 #include <cub/iterator/counting_input_iterator.cuh>
 #include <cub/iterator/transform_input_iterator.cuh>
@@ -126,7 +126,7 @@ project_kernel(int P,
                bool means_al16, bool scales_al16, bool rot_al16,
                int32_t* __restrict__ radii, uint32_t* __restrict__ depth_key,
                uint32_t* __restrict__ tiles_touched, float4* __restrict__ geomA,
-               float4* __restrict__ geomB, uint2* __restrict__ rect, uint32_t* __restrict__ iota) {
+               float4* __restrict__ geomB, uint2* __restrict__ rect) {
     __shared__ __align__(16) float s_mean[kProjThreads * 3];
     __shared__ __align__(16) float s_scale[kProjThreads * 3];
     __shared__ float s_vm[16], s_pm[16];
@@ -154,7 +154,6 @@ project_kernel(int P,
             radii[gidx] = 0;
             depth_key[gidx] = kCulledKey;
             tiles_touched[gidx] = 0u;
-            iota[gidx] = (uint32_t)gidx;
         }
     }
     const uint32_t ball = __ballot_sync(0xffffffffu, front);
@@ -253,7 +252,6 @@ project_kernel(int P,
     radii[idx] = out_radius;
     depth_key[idx] = out_key;
     tiles_touched[idx] = out_tiles;
-    iota[idx] = (uint32_t)idx;
     if (out_tiles != 0u) {          // geomA / geomB / rect are only ever read for Gaussians that touch a tile
         geomA[idx] = gA;
         geomB[idx] = gB;
@@ -288,15 +286,13 @@ struct TilesInDepthOrder {
 
 }  // namespace
 
-size_t geometry_cub_temp_bytes(int P) {
-    size_t sort_bytes = 0, scan_bytes = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr,
-                                    (const uint32_t*)nullptr, (uint32_t*)nullptr, P);
+size_t geometry_scan_temp_bytes(int P) {
+    size_t scan_bytes = 0;
     TilesInDepthOrder op{nullptr, nullptr};
     cub::TransformInputIterator<uint32_t, TilesInDepthOrder, cub::CountingInputIterator<uint32_t>> it(
         cub::CountingInputIterator<uint32_t>(0u), op);
     cub::DeviceScan::InclusiveSum(nullptr, scan_bytes, it, (uint32_t*)nullptr, P);
-    return sort_bytes > scan_bytes ? sort_bytes : scan_bytes;
+    return scan_bytes;
 }
 
 int launch_project(const sb_settings& s, int P, const float* means3D, const float* opacities,
@@ -311,7 +307,7 @@ int launch_project(const sb_settings& s, int P, const float* means3D, const floa
         P, means3D, opacities, scales, reinterpret_cast<const float4*>(rotations), cov3D_precomp,
         s.viewmatrix, s.projmatrix, W, H, s.tanfovx, s.tanfovy, focal_x, focal_y, s.scale_modifier,
         gx, gy, s.prefiltered != 0, al16(means3D), al16(scales), al16(rotations),
-        radii, g.depth_key, g.tiles_touched, g.geomA, g.geomB, g.rect, g.iota);
+        radii, g.depth_key, g.tiles_touched, g.geomA, g.geomB, g.rect);
     SB_LAUNCH_CHECK("project_kernel");
     return SB_OK;
 }
@@ -321,16 +317,17 @@ int launch_project(const sb_settings& s, int P, const float* means3D, const floa
 // reproduces the reference's single 64-bit (tile|depth) sort of rasterizer_impl.cu:304-309 exactly
 // (ties in the reference resolve by emission order == Gaussian index).
 int launch_depth_order(int P, const GeometryWs& g, cudaStream_t st) {
-    size_t tb = g.cub_temp_bytes;
     { ScopedStage _p(kStDepthSort, st);
-      SB_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(g.cub_temp, tb, g.depth_key, g.sorted_key, g.iota,
-                                                    g.sorted_idx, P, 0, 32, st)); }
+      // payload = the Gaussian's index, synthesised by the first pass; depth_key is left intact
+      const int rc = radix_sort_pairs(g.depth_key, nullptr, g.sorted_key, g.sorted_idx, P, nullptr, 0, 32, g.sort_temp,
+                                      g.sort_temp_bytes, st);
+      if (rc != SB_OK) return rc; }
     TilesInDepthOrder op{g.tiles_touched, g.sorted_idx};
     cub::TransformInputIterator<uint32_t, TilesInDepthOrder, cub::CountingInputIterator<uint32_t>> it(
         cub::CountingInputIterator<uint32_t>(0u), op);
-    tb = g.cub_temp_bytes;
+    size_t tb = g.scan_temp_bytes;
     ScopedStage _p(kStDepthScan, st);
-    SB_CUDA_CHECK(cub::DeviceScan::InclusiveSum(g.cub_temp, tb, it, g.offsets, P, st));
+    SB_CUDA_CHECK(cub::DeviceScan::InclusiveSum(g.scan_temp, tb, it, g.offsets, P, st));
     return SB_OK;
 }
 

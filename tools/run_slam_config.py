@@ -35,7 +35,7 @@ import scenes  # noqa: E402
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--config", type=int, choices=[4, 5], required=True)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "ours-plain", "reference"])
     ap.add_argument("--frames", type=int, default=0)
     ap.add_argument("--gaussians", type=int, default=0)
     ap.add_argument("--tracking-iters", type=int, default=0)
@@ -51,8 +51,9 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     import bench
     from splatam_b200 import slam
-    Rast, Settings = bench.get_ops(a.impl)
+    Rast, Settings = bench.get_ops("reference" if a.impl == "reference" else "ours")
     assert Rast is not None, "reference extension not installed under baseline/_ref"
+    # ours-plain: this repo's operator behind the PyTorch glue / torch Adam (separates operator from fused-glue effects)
     render = None if a.impl == "ours" else (lambda settings, **rv: Rast(raster_settings=settings)(**rv))
     fused = a.impl == "ours"
     torch.manual_seed(0); np.random.seed(0)
