@@ -37,7 +37,8 @@ def parse():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "cpu"])
-    ap.add_argument("--workload", default="config3", choices=["config3", "room50k", "tum3m", "config1"])
+    ap.add_argument("--workload", default="config3",
+                    choices=["config3", "replica50k", "splatam816k", "tum3m", "room50k", "room3m", "config1"])
     ap.add_argument("--gaussians", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-mapping", action="store_true")
@@ -48,11 +49,20 @@ def parse():
 def make_scene(args):
     if args.workload == "config3":
         return scenes.config3(P=args.gaussians or 1_000_000), "config3: synthetic isotropic Gaussians, Replica intrinsics 1200x680, seed 2"
-    if args.workload == "room50k":
+    if args.workload == "replica50k":      # BASELINE config[1] geometry: ~50k Gaussians that fill a 1200x680 view
+        return scenes.view_filling(seed=12, P=args.gaussians or 50_000, cover=True), \
+            "replica50k: 50k isotropic Gaussians covering the view (splat size = pixel spacing), Replica intrinsics 1200x680, seed 12"
+    if args.workload == "splatam816k":     # SplaTAM's own first-frame map: one Gaussian per pixel (splatam.py:196-203)
+        return scenes.view_filling(seed=12, P=args.gaussians or None), \
+            "splatam816k: one isotropic Gaussian per pixel (sigma 1 px, opacity ~0.5), Replica intrinsics 1200x680, seed 12"
+    if args.workload == "tum3m":           # BASELINE config[4] geometry: 3M anisotropic Gaussians, all in view
+        return scenes.view_filling(seed=15, P=args.gaussians or 3_000_000, cam=scenes.TUM_FR1, anisotropic=True), \
+            "tum3m: 3M anisotropic Gaussians filling the view, TUM fr1 intrinsics 640x480, seed 15"
+    if args.workload == "room50k":         # round-1 workloads (97 % of the Gaussians outside the frustum), kept for continuity
         return scenes.room(P=args.gaussians or 50_000), "room: ~50k isotropic Gaussians, Replica intrinsics 1200x680, seed 1"
-    if args.workload == "tum3m":
+    if args.workload == "room3m":
         return scenes.room(seed=9, P=args.gaussians or 3_000_000, cam=scenes.TUM_FR1, anisotropic=True), \
-            "tum3m: anisotropic Gaussians, TUM fr1 intrinsics 640x480, seed 9"
+            "room3m: anisotropic Gaussians, TUM fr1 intrinsics 640x480, seed 9 (~10 % in view)"
     return scenes.config1(), "config1: 256 Gaussians 64x64"
 
 
@@ -532,7 +542,11 @@ def main():
             return
         cb, P_s, R_s = cpu_oracle_run(scene)
         # the brute-force PyTorch composite is O(P x pixels): timed on small prefixes of the workload, never extrapolated
-        cb["bruteforce_torch"] = [cpu_bruteforce_run(scene, n) for n in (256, 1024) if n <= scene.P]
+        # BASELINE.md B2 names P in {256, 4096, 65536}: the first two are timed; 65536 Gaussians x 816k pixels is 5.3e10 pair
+        # evaluations (hours on these host cores) and is reported as not run rather than extrapolated
+        cb["bruteforce_torch"] = [cpu_bruteforce_run(scene, n) for n in (256, 4096) if n <= scene.P]
+        cb["bruteforce_torch_not_run"] = {"gaussians": 65536, "pair_evals": 65536 * scene.w * scene.h,
+                                          "why": "beyond the time budget of one bench invocation; no extrapolation reported"}
         line = dict(base, impl="cpu", value=cb["value"], ms_per_step=1000.0 / cb["value"], n_gpus=0,
                     config=dict(workload=wl_desc, sample=cb["sample"]), cpu_baseline=cb,
                     e2e=dict(value=cb["value"], unit="renders/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
@@ -574,8 +588,17 @@ def main():
         estep, h2d, d2h, begin, finish, enote, lanes = e2e_graph_step_fn(scene, dev, Rast, Settings, mode["max_rendered"])
     else:
         estep, h2d, d2h, begin, finish, enote = e2e_step_fn(scene, dev, Rast, Settings)
-    ems = timed(estep, e_steps, 4, dev, dist_on, sampler=sampler, begin=begin, finish=finish) / e_steps
+    # median of three timed regions: the end-to-end leg depends on the host (graph launches, PCIe), which varies more
+    # from box to box than the device-resident metric
+    e_runs = sorted(timed(estep, e_steps, 4, dev, dist_on, sampler=sampler, begin=begin, finish=finish) / e_steps
+                    for _ in range(3))
+    ems = e_runs[1]
     clocks = sampler.stop()
+    eager_ms = None
+    if args.impl == "ours" and not args.eager:
+        # what UNMODIFIED SplaTAM gets: Renderer(raster_settings=cam)(**rendervar) -> the synchronous operator with
+        # the num_rendered read-back every forward (no capacity argument, no CUDA graph)
+        eager_ms = timed(eager_step, max(args.steps // 2, 4), 3, dev, dist_on) / max(args.steps // 2, 4)
     if "max_rendered" in mode:
         n_r, overflow = Rast.last_counts()
         assert not overflow and n_r == R, f"e2e sync-free capacity check failed: {n_r} {overflow} expected {R}"
@@ -586,7 +609,12 @@ def main():
 
     b_algo = scenes.algorithmic_bytes(scene.P, R, scene.w, scene.h)
     peak, peak_src = load_peaks()
+    e2e["runs_ms_per_step"] = [round(x, 4) for x in e_runs]
     line = dict(base, value=value, ms_per_step=ms_per_step, e2e=e2e, clocks=clocks)
+    if eager_ms is not None:
+        line["eager_drop_in"] = dict(value=world * 1000.0 / eager_ms, unit="renders/s", ms_per_step=eager_ms,
+                                     note="the synchronous operator exactly as unmodified SplaTAM calls it (num_rendered "
+                                          "read back every forward, ~25 launches, no CUDA graph); host-speed dependent")
     line["config"] = dict(workload=wl_desc, gaussians=scene.P, width=scene.w, height=scene.h, num_rendered=R,
                           parallelism=f"replicas x{world}", mode=mode["mode"],
                           l2="per-step working set (inputs 56 B/Gaussian + geometry/binning/record workspaces, "
@@ -625,9 +653,13 @@ def main():
             "geometry_backward": 56 * scene.P + 36 * scene.P + 68 * scene.P,
         }
         ach = stage_bytes[top] / (stages[top] * 1e-3) / 1e9
-        # dram__bytes_read.sum + dram__bytes_write.sum per launch of blend_backward from the committed ncu --set full
-        # capture of this exact workload (profiles/r01_blend_final_ncu_full.txt); null for any other workload
-        traffic = 212.46e6 if (args.workload == "config3" and scene.P == 1_000_000 and top == "blend_backward") else None
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the committed
+        # ncu --set full capture of this exact workload (profiles/r02_traffic.json, written by tools/ncu_traffic.py from
+        # the .ncu-rep); null for any other workload
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "r02_traffic.json")
+        if args.workload == "config3" and scene.P == 1_000_000 and os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get("ours", {}).get(top, {}).get("dram_bytes")
         line["roofline"] = dict(bound="hbm", kernel=top, achieved=ach, peak=peak, unit="GB/s", frac=ach / peak,
                                 traffic=traffic, peak_source=peak_src, kernel_ms=stages[top],
                                 algorithmic_bytes_per_launch=stage_bytes[top],
@@ -635,12 +667,12 @@ def main():
                                             frac=b_algo / (ms_per_step * 1e-3) / 1e9 / peak,
                                             note="whole fwd+bwd render, B_algo of SURVEY.md 8(d)"),
                                 stage_ms={k: round(v, 4) for k, v in stages.items()})
-        own = 6 if args.eager else 8
+        own = 15 if args.eager else 16
         line["gpu_launches"] = own * args.steps
         line["config"]["gpu_launches_note"] = (
-            "%d hand-written kernels per step (project, emit_instances, ranges_records, blend_forward, blend_backward, "
-            "geometry_backward%s); CUB radix sort/scan kernels and 2 memsets not counted"
-            % (own, "" if args.eager else ", plus finalize_count and pad_tiles of the sync-free mode"))
+            "%d hand-written kernels per step: project, depth sort (radix_hist + 4 radix_onesweep passes), emit_instances, "
+            "tile sort (radix_hist + 2 passes), ranges_records, blend_forward, blend_backward, geometry_backward%s; the CUB "
+            "inclusive scan and 3 memsets are not counted" % (own, "" if args.eager else ", finalize_count of the sync-free mode"))
         if rank == 0 and world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"], _, _ = cpu_oracle_run(scene)
     if not args.no_mapping:

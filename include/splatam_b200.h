@@ -186,12 +186,13 @@ SB_API int sb_backward_ex(const sb_settings* s, int P, int num_rendered, const f
 /* ---- spherical-harmonics colour branch (shs / sh_degree, X/cuda_rasterizer/forward.cu:20-71,
  *      backward.cu:20-139).  sb_sh_forward turns shs [P,max_coeffs,3] into the rgb [P,3] the render consumes
  *      (plus one clamp-flag byte per Gaussian); sb_sh_backward turns dL/drgb into dL/dshs and ADDS the
- *      view-direction term to dL_dmeans3D.  Unused by SplaTAM. */
+ *      view-direction term to dL_dmeans3D; Gaussians with radii[i] <= 0 (when `radii` is not NULL) get zero gradients,
+ *      as the reference leaves them.  Unused by SplaTAM. */
 SB_API int sb_sh_forward(int P, int sh_degree, int max_coeffs, const float* means3D, const float* campos,
                          const float* shs, float* rgb, uint8_t* clamped, void* stream);
 SB_API int sb_sh_backward(int P, int sh_degree, int max_coeffs, const float* means3D, const float* campos,
-                          const float* shs, const uint8_t* clamped, const float* dL_drgb, float* dL_dshs,
-                          float* dL_dmeans3D_accumulate, void* stream);
+                          const float* shs, const uint8_t* clamped, const float* dL_drgb, const int32_t* radii,
+                          float* dL_dshs, float* dL_dmeans3D_accumulate, void* stream);
 
 /* ---- markVisible (X/cuda_rasterizer/rasterizer_impl.cu:54-66,141-153) ------------------- */
 SB_API int sb_mark_visible(int P, const float* means3D, const float* viewmatrix,

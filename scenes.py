@@ -155,7 +155,8 @@ def _surface_depth(u, v):
     return 2.5 + 0.8 * torch.sin(u / 130.0) * torch.cos(v / 90.0) + 0.3 * torch.sin(u / 23.0 + v / 31.0)
 
 
-def view_filling(seed=12, cam=REPLICA, P=None, stride=1, anisotropic=False, w2c=None, opacity=(0.45, 0.6), margin=0):
+def view_filling(seed=12, cam=REPLICA, P=None, stride=1, anisotropic=False, w2c=None, opacity=(0.45, 0.6), margin=0,
+                 cover=False):
     """A map that FILLS the view the way SplaTAM's maps do: one Gaussian per pixel of the first frame,
     back-projected through the depth map, sigma_world = depth / f (one pixel std on screen), logit opacity ~ 0
     (R/scripts/splatam.py:67-118,120-157,196-203: get_pointcloud + initialize_params with the "projective"
@@ -174,7 +175,9 @@ def view_filling(seed=12, cam=REPLICA, P=None, stride=1, anisotropic=False, w2c=
     if P < n_grid:
         keep = torch.randperm(n_grid, generator=g)[:P].sort().values
         u, v = u[keep], v[keep]
-        size = torch.ones(P)
+        # cover: a map with fewer Gaussians than pixels still fills the view (as a map built at a lower densification
+        # resolution does): splat size grows with the pixel spacing
+        size = torch.full((P,), math.sqrt(n_grid / P) if cover else 1.0)
     else:
         extra = P - n_grid
         u = torch.cat([u, -margin + (w + 2 * margin) * _rand(g, extra)])

@@ -76,7 +76,7 @@ _SIGNATURES = {
     "sb_prepare_forward": (_i, [_i, _i] + [_vp] * 12 + [_vp]),
     "sb_prepare_backward": (_i, [_i, _i, _i] + [_vp] * 18 + [_vp]),
     "sb_sh_forward": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "sb_sh_backward": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "sb_sh_backward": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sb_masked_l1_forward": (_i, [_vp, _vp, _vp, _vp, _i, _i, ctypes.c_float, _i, _vp, _vp]),
     "sb_masked_l1_backward": (_i, [_vp, _vp, _vp, _vp, _i, _i, ctypes.c_float, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sb_prune_mask": (_i, [_i, _vp, _vp, _i, ctypes.c_float, ctypes.c_float, _vp, _vp]),

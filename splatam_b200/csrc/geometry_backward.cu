@@ -26,7 +26,7 @@ __device__ __forceinline__ void copy_out(float* __restrict__ dst, const float* _
     for (int i = done + tid; i < n; i += 256) d[i] = stage[i];
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 geometry_backward_kernel(int P, const float* __restrict__ means3D, const float* __restrict__ colors,
                          const float* __restrict__ scales, const float* __restrict__ rotations,
                          const float* __restrict__ cov3D_precomp, const int32_t* __restrict__ radii,

@@ -30,8 +30,8 @@ namespace {
 constexpr int kBins = 256;
 constexpr int kSortThreads = 256;
 constexpr int kSortWarps = kSortThreads / 32;
-constexpr int kItems = 16;
-constexpr int kTileItems = kSortThreads * kItems;      // 4096
+constexpr int kItemsLarge = 16, kItemsSmall = 8;       // keys per thread: 4096- or 2048-key tiles
+constexpr int kSmallSortLimit = 64 << 10;              // tiny inputs only: measured on B200, 2048-key tiles lose to 4096-key tiles at 1M keys
 constexpr int kMaxPasses = 4;
 constexpr uint32_t kFlagAgg = 1u << 30, kFlagInc = 2u << 30, kValMask = (1u << 30) - 1u;
 
@@ -46,9 +46,12 @@ struct RadixTemp {
     int tiles;
 };
 
+inline int tile_items_for(int capacity) { return kSortThreads * (capacity <= kSmallSortLimit ? kItemsSmall : kItemsLarge); }
+
 RadixTemp radix_layout(void* temp, int capacity, int passes) {
     RadixTemp t;
     Carver c(temp);
+    const int kTileItems = tile_items_for(capacity);
     t.tiles = (capacity + kTileItems - 1) / kTileItems;
     t.hist = c.take<uint32_t>((size_t)kMaxPasses * kBins);
     t.tickets = c.take<uint32_t>(64);
@@ -108,12 +111,13 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* s
     return base + inc - v;
 }
 
-template <bool IOTA>
+template <bool IOTA, int kItems>
 __global__ void __launch_bounds__(kSortThreads)
 radix_onesweep_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                       uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int capacity,
                       const int32_t* __restrict__ n_dev, int shift, uint32_t mask, const uint32_t* __restrict__ hist,
                       uint32_t* __restrict__ ticket, uint32_t* __restrict__ status) {
+    constexpr int kTileItems = kSortThreads * kItems;
     __shared__ uint32_t s_keys[kTileItems];
     __shared__ uint32_t s_vals[kTileItems];
     __shared__ uint32_t s_whist[kSortWarps][kBins];
@@ -167,11 +171,27 @@ radix_onesweep_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __re
         st_relaxed(my, kFlagInc | count);
     } else {
         st_relaxed(my, kFlagAgg | count);
-        for (long long t = (long long)tile - 1; t >= 0; --t) {
-            uint32_t s;
-            do { s = ld_relaxed(status + (size_t)t * kBins + tid); } while ((s >> 30) == 0u);
-            prev += s & kValMask;
-            if ((s >> 30) == 2u) break;
+        // walk back over the predecessors, kLook status words in flight at a time (the loads are independent, so their
+        // L2 latencies overlap; a strictly serial walk costs one round trip per predecessor tile)
+        constexpr int kLook = 8;
+        long long t = (long long)tile - 1;
+        bool done = false;
+        while (t >= 0 && !done) {
+            const int nb = (int)min((long long)kLook, t + 1);
+            uint32_t sw[kLook];
+#pragma unroll
+            for (int i = 0; i < kLook; ++i)
+                sw[i] = i < nb ? ld_relaxed(status + (size_t)(t - i) * kBins + tid) : 0u;
+#pragma unroll
+            for (int i = 0; i < kLook; ++i) {
+                if (i < nb && !done) {
+                    uint32_t sv = sw[i];
+                    while ((sv >> 30) == 0u) sv = ld_relaxed(status + (size_t)(t - i) * kBins + tid);
+                    prev += sv & kValMask;
+                    done = (sv >> 30) == 2u;
+                }
+            }
+            t -= nb;
         }
         st_relaxed(my, kFlagInc | (prev + count));
     }
@@ -229,12 +249,16 @@ int radix_sort_pairs(const uint32_t* keys_in, const uint32_t* vals_in, uint32_t*
         const int lo = begin_bit + 8 * p, width = min(8, end_bit - lo);
         const uint32_t mask = (1u << width) - 1u;
         uint32_t* status = t.status + (size_t)p * (size_t)t.tiles * kBins;
-        if (p == 0 && vals_in == nullptr)
-            radix_onesweep_kernel<true><<<t.tiles, kSortThreads, 0, st>>>(src_k, nullptr, dst_k, dst_v, capacity, n_dev, lo,
-                                                                          mask, t.hist + p * kBins, t.tickets + p, status);
-        else
-            radix_onesweep_kernel<false><<<t.tiles, kSortThreads, 0, st>>>(src_k, src_v, dst_k, dst_v, capacity, n_dev, lo,
-                                                                           mask, t.hist + p * kBins, t.tickets + p, status);
+#define SB_SORT_PASS(IOTA, ITEMS)                                                                                   \
+        radix_onesweep_kernel<IOTA, ITEMS><<<t.tiles, kSortThreads, 0, st>>>(src_k, IOTA ? nullptr : src_v, dst_k, dst_v,  \
+                                                                             capacity, n_dev, lo, mask, t.hist + p * kBins, \
+                                                                             t.tickets + p, status)
+        const bool iota = (p == 0 && vals_in == nullptr), small = capacity <= kSmallSortLimit;
+        if (iota && small) SB_SORT_PASS(true, kItemsSmall);
+        else if (iota) SB_SORT_PASS(true, kItemsLarge);
+        else if (small) SB_SORT_PASS(false, kItemsSmall);
+        else SB_SORT_PASS(false, kItemsLarge);
+#undef SB_SORT_PASS
         SB_LAUNCH_CHECK("radix_onesweep_kernel");
         src_k = dst_k;
         src_v = dst_v;

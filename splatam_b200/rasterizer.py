@@ -323,7 +323,8 @@ class _RasterizeGaussians(torch.autograd.Function):
             with torch.cuda.device(means3D.device):
                 _lib.check(_lib.load().sb_sh_backward(means3D.shape[0], deg, M, means3D.data_ptr(), campos.data_ptr(),
                                                       sh_c.data_ptr(), clamped.data_ptr(), g_colors.data_ptr(),
-                                                      g_sh.data_ptr(), g_means3D.data_ptr(), _stream(means3D.device)),
+                                                      radii.data_ptr(), g_sh.data_ptr(), g_means3D.data_ptr(),
+                                                      _stream(means3D.device)),
                            "sb_sh_backward")
             return (g_means3D, g_means2D, g_sh.reshape(sh_shape), None, g_opac.reshape(ctx.opac_shape),
                     g_scales if not needs_cov else None, g_rot if not needs_cov else None,

@@ -47,6 +47,11 @@ def _check_against(ours, ref, exact_images, tag, grad_tol=REL):
         assert (rel_err(ours["final_T"], ref["final_T"], 1e-3) > REL).mean() < 1e-3, tag
     for k in GRADS:
         a, b = ours["grad_" + k].reshape(-1), ref["grad_" + k].reshape(-1)
+        if k == "rotations" and np.abs(b).max() < 1e-6 * np.abs(ref["grad_scales"]).max():
+            # isotropic scene: the quaternion gradient is mathematically zero and pure cancellation noise (~1e-10) in
+            # every implementation (the reference's two runs differ by ~100 % here); only its smallness is meaningful
+            assert np.abs(a).max() < 1e-6 * np.abs(ref["grad_scales"]).max(), (tag, k)
+            continue
         assert l2_rel(a, b) < grad_tol, (tag, k, l2_rel(a, b))
         # element-wise: entries that are sums with heavy cancellation carry float32 summation-order noise
         # (the reference's own atomics are order-nondeterministic), so floor at 1e-3 of the largest entry
@@ -91,7 +96,10 @@ def test_cuda_vs_golden(path, cuda_device):
 
 BIG = [("config1", scenes.config1), ("edge", scenes.edge_cases), ("dense", lambda: scenes.dense_opaque()),
        ("room50k", lambda: scenes.room(P=50_000)), ("tum_aniso", lambda: scenes.room(seed=9, P=200_000, cam=scenes.TUM_FR1, anisotropic=True)),
-       ("config3_1M", lambda: scenes.config3())]
+       ("config3_1M", lambda: scenes.config3()),
+       ("splatam816k", lambda: scenes.view_filling(seed=12)),            # one Gaussian per pixel: every Gaussian in view
+       ("replica50k", lambda: scenes.view_filling(seed=12, P=50_000, cover=True)),
+       ("tum3m_aniso", lambda: scenes.view_filling(seed=15, P=3_000_000, cam=scenes.TUM_FR1, anisotropic=True))]
 
 
 @pytest.mark.parametrize("name,make", BIG)
@@ -106,6 +114,52 @@ def test_cuda_vs_reference_extension(name, make, cuda_device):
     ref2 = run_ref(sc, dL)  # the reference's own run-to-run atomics noise calibrates the gradient bound
     noise = max(l2_rel(ref2["grad_" + k], ref["grad_" + k]) for k in GRADS)
     _check_against(ours, ref, exact_images=True, tag=name, grad_tol=max(REL, 4 * noise))
+
+
+def _err_stats(a, b):
+    """Element-wise relative error with the SURVEY floor (1e-6 of the largest entry) + L2-relative error."""
+    e = rel_err(a, b, 1e-6).reshape(-1)
+    return dict(l2_rel=l2_rel(a, b), p50=float(np.percentile(e, 50)), p99=float(np.percentile(e, 99)),
+                p999=float(np.percentile(e, 99.9)), max=float(e.max()), frac_gt_1e4=float((e > 1e-4).mean()),
+                frac_gt_1e3=float((e > 1e-3).mean()))
+
+
+def test_gradients_vs_double_oracle_full_size(cuda_device):
+    """BASELINE config[2] (1M Gaussians, 1200x680): all six gradients against the C oracle, whose backward
+    accumulates in DOUBLE and is deterministic, element by element.  The same statistics are taken for the reference
+    extension (float atomics) so the numbers can be read side by side; everything measured is written to
+    gpurun_out/r02_gradient_parity.json (committed under profiles/)."""
+    import json
+    from gpu_harness import random_dL, run_ours, run_ref
+    sc = scenes.config3()
+    dL = random_dL(sc)
+    ours = run_ours(sc, dL, intermediates=False)
+    o = sc.oracle()
+    o.render()
+    og = o.backward(dL)
+    report = {"workload": "config3 1M Gaussians 1200x680", "floor": "1e-6 x max|reference entry|", "ours_vs_oracle": {},
+              "reference_vs_oracle": {}, "reference_run_to_run": {}}
+    have_ref = reference_extension() is not None
+    if have_ref:
+        r1, r2 = run_ref(sc, dL), run_ref(sc, dL)
+    for k in GRADS:
+        if k == "rotations":      # isotropic scene: mathematically zero, float noise in every implementation
+            continue
+        report["ours_vs_oracle"][k] = _err_stats(ours["grad_" + k], og[k])
+        if have_ref:
+            report["reference_vs_oracle"][k] = _err_stats(r1["grad_" + k], og[k])
+            report["reference_run_to_run"][k] = _err_stats(r2["grad_" + k], r1["grad_" + k])
+    os.makedirs(os.path.join(os.path.dirname(GOLDEN), "..", "gpurun_out"), exist_ok=True)
+    with open(os.path.join(os.path.dirname(GOLDEN), "..", "gpurun_out", "r02_gradient_parity.json"), "w") as f:
+        json.dump(report, f, indent=1)
+    for k, st in report["ours_vs_oracle"].items():
+        assert st["l2_rel"] < REL, (k, st)
+        # element-wise: float32 sums with cancellation cannot hold 1e-4 on every entry (the reference's own atomics
+        # do not either); the bulk must, and the tail must not be worse than the reference's tail
+        assert st["p50"] < REL and st["frac_gt_1e3"] < 2e-3, (k, st)
+        if have_ref:
+            rs = report["reference_vs_oracle"][k]
+            assert st["p99"] <= max(2.0 * rs["p99"], REL), (k, st, rs)
 
 
 def test_full_size_properties(cuda_device):
