@@ -32,20 +32,19 @@ namespace sb {
 namespace {
 
 constexpr int kBatch = 64;            // records per ring stage
-constexpr int kStages = 8;
+template <int NCH> constexpr int stages_of() { return NCH == 6 ? 4 : 8; }   // ring depth (4 record arrays per stage at NCH 6)
 constexpr int kConsumerWarps = 8;
 constexpr int kBlendThreads = (kConsumerWarps + 1) * 32;
 constexpr int kRow = 33;              // matrix row stride in cells: column sweeps (reduce) are conflict-free
 
-// One matrix cell per (window slot, pixel).
-//   NCH == 3: {opacity*G -> w, c.dL -> ca}
-//   NCH == 6: {opacity*G -> w (both colour sets), (c.dL + e.dL2) -> ca, c.dL -> w of the first set, -}
-template <int NCH> struct CellT { using type = float2; };
-template <> struct CellT<6> { using type = float4; };
+// One matrix cell per (window slot, pixel): {opacity*G -> w, c.dL -> ca}; for NCH == 6 the cell holds the sums over
+// both colour sets {opacity*G -> w, (c.dL + e.dL2) -> ca} and a second float matrix q3 holds {c.dL -> w of the first
+// set}.  12 B per (slot, pixel) instead of a padded float4 keeps two CTAs per SM resident.
+using Cell = float2;
 
 template <int NCH, int KW>
 struct __align__(128) BwdSmem {
-    using Cell = typename CellT<NCH>::type;
+    static constexpr int kStages = stages_of<NCH>();
     float4 A[kStages][kBatch];
     float4 B[kStages][kBatch];
     float4 C[kStages][kBatch];
@@ -61,6 +60,7 @@ struct __align__(128) BwdSmem {
     float4 WD[NCH == 6 ? kConsumerWarps : 1][NCH == 6 ? KW : 1];   // second colour set
     // ... the [slot][pixel] matrix and dL/dpixel of the warp's 32 pixels
     Cell q[kConsumerWarps][KW][kRow];
+    float q3[NCH == 6 ? kConsumerWarps : 1][NCH == 6 ? KW : 1][kRow];
     float4 dL[kConsumerWarps][NCH == 6 ? 2 : 1][32];
 };
 
@@ -96,11 +96,11 @@ __device__ __forceinline__ void process_window(BwdSmem<NCH, KW>& sm, const int w
                                                const float bg_dot, const float bg_dot1, PixelState<NCH>& st,
                                                const float fx0, const float fy0, const float ddelx_dx,
                                                const float ddely_dy, float* __restrict__ accum) {
-    using Cell = typename CellT<NCH>::type;
     constexpr uint32_t full = 0xffffffffu;
     constexpr int kStride = NCH == 6 ? kAccumStride2 : kAccumStride;
     __syncwarp();
     Cell* const qcol = &sm.q[warp][0][lane];          // this pixel's column, row stride kRow cells
+    float* const q3col = &sm.q3[NCH == 6 ? warp : 0][0][lane];
 
     // ---- evaluate: lock-step over the slots, lane = pixel (same float sequence as the forward so the skip
     //      decisions agree, backward.cu:491-500) ----
@@ -125,13 +125,14 @@ __device__ __forceinline__ void process_window(BwdSmem<NCH, KW>& sm, const int w
         const float cd1 = fmaf(col.z, dLa.z, fmaf(col.y, dLa.y, col.x * dLa.x));
         if constexpr (NCH == 6) {
             const float cdS = fmaf(ex.z, dLb.z, fmaf(ex.y, dLb.y, fmaf(ex.x, dLb.x, cd1)));
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (active) { v.x = Gop; v.y = cdS; v.z = cd1; }
-            *reinterpret_cast<float4*>(qcol + s * kRow) = v;
+            float2 v = make_float2(0.f, 0.f);
+            if (active) { v.x = Gop; v.y = cdS; }
+            qcol[s * kRow] = v;
+            q3col[s * kRow] = active ? cd1 : 0.f;
         } else {
             float2 v = make_float2(0.f, 0.f);
             if (active) { v.x = Gop; v.y = cd1; }
-            *reinterpret_cast<float2*>(qcol + s * kRow) = v;
+            qcol[s * kRow] = v;
         }
         mymask |= (active ? 1u : 0u) << s;
         wa = wa_n; q = q_n; col = col_n; ex = ex_n;
@@ -141,13 +142,15 @@ __device__ __forceinline__ void process_window(BwdSmem<NCH, KW>& sm, const int w
     const int iters = (int)__reduce_max_sync(full, (uint32_t)__popc(mymask));
     {
         // the next contributor's cell is loaded before this one's chain step (hides the shared-memory latency)
-        Cell* cell = qcol + (mymask != 0u ? __ffs(mymask) - 1 : 0) * kRow;
-        Cell v = *cell;
+        int so = (mymask != 0u ? __ffs(mymask) - 1 : 0) * kRow;
+        Cell v = qcol[so];
+        float v3 = NCH == 6 ? q3col[so] : 0.f;
         for (int it = 0; it < iters; ++it) {
             const bool on = mymask != 0u;
             mymask &= mymask - 1u;
-            Cell* const cell_n = qcol + (mymask != 0u ? __ffs(mymask) - 1 : 0) * kRow;
-            const Cell v_n = *cell_n;
+            const int so_n = (mymask != 0u ? __ffs(mymask) - 1 : 0) * kRow;
+            const Cell v_n = qcol[so_n];
+            const float v3_n = NCH == 6 ? q3col[so_n] : 0.f;
             if (on) {
                 const float Gop = v.x, cd = v.y;
                 const float alpha = fminf(Gop, 0.99f);
@@ -160,17 +163,16 @@ __device__ __forceinline__ void process_window(BwdSmem<NCH, KW>& sm, const int w
                 const float dL_dalpha = fmaf(cd - st.A, st.T, -tb * bg_dot);
                 st.last_cd = cd;
                 if constexpr (NCH == 6) {
-                    const float cd1 = reinterpret_cast<const float4&>(v).z;
+                    const float cd1 = v3;
                     st.A1 = fmaf(st.last_alpha, st.last_cd1, om * st.A1);
                     const float dL_dalpha1 = fmaf(cd1 - st.A1, st.T, -tb * bg_dot1);
                     st.last_cd1 = cd1;
-                    *reinterpret_cast<float4*>(cell) = make_float4(Gop * dL_dalpha, ca, Gop * dL_dalpha1, 0.f);
-                } else {
-                    *reinterpret_cast<float2*>(cell) = make_float2(Gop * dL_dalpha, ca);
+                    q3col[so] = Gop * dL_dalpha1;
                 }
+                qcol[so] = make_float2(Gop * dL_dalpha, ca);
                 st.last_alpha = alpha;
             }
-            cell = cell_n; v = v_n;
+            so = so_n; v = v_n; v3 = v3_n;
         }
     }
     __syncwarp();
@@ -200,7 +202,7 @@ __device__ __forceinline__ void process_window(BwdSmem<NCH, KW>& sm, const int w
             Sxx = fmaf(wdx, dx, Sxx); Sxy = fmaf(wdx, dy, Sxy); Syy = fmaf(wdy, dy, Syy);
             C0 = fmaf(ca, d.x, C0); C1 = fmaf(ca, d.y, C1); C2 = fmaf(ca, d.z, C2);
             if constexpr (NCH == 6) {
-                const float wr = reinterpret_cast<const float4&>(v).z;
+                const float wr = sm.q3[NCH == 6 ? warp : 0][NCH == 6 ? sc : 0][16 * part + it];
                 const float4 d2 = sm.dL[warp][NCH == 6 ? 1 : 0][16 * part + it];
                 Rx = fmaf(wr, dx, Rx); Ry = fmaf(wr, dy, Ry);
                 E0 = fmaf(ca, d2.x, E0); E1 = fmaf(ca, d2.y, E1); E2 = fmaf(ca, d2.z, E2);
@@ -248,6 +250,7 @@ blend_backward_kernel(const uint2* __restrict__ ranges, const float4* __restrict
     extern __shared__ __align__(128) unsigned char smem_raw[];
     BwdSmem<NCH, KW>& sm = *reinterpret_cast<BwdSmem<NCH, KW>*>(smem_raw);
     constexpr uint32_t full = 0xffffffffu;
+    constexpr int kStages = stages_of<NCH>();
     const uint32_t tile = blockIdx.x;
     const uint2 range = ranges[tile];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

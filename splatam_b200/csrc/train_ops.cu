@@ -37,13 +37,18 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
             size_t n, AdamSegs segs, float w1, float beta2, float w2, float eps, float bc2_sqrt,
             const AdamClock* __restrict__ clk, const float* __restrict__ skip_if_nonzero) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ float s_neg[kMaxSeg + 1];      // guarded mode: the clock's step sizes, fetched once per CTA
+    if (GUARDED) {
+        if (skip_if_nonzero != nullptr && __ldg(skip_if_nonzero) != 0.f) return;      // uniform over the grid
+        if (threadIdx.x <= kMaxSeg) s_neg[threadIdx.x] = threadIdx.x < kMaxSeg ? clk->neg_step[threadIdx.x] : clk->bc2_sqrt;
+        __syncthreads();
+        bc2_sqrt = s_neg[kMaxSeg];
+    }
     if (i >= n) return;
-    if (GUARDED && skip_if_nonzero != nullptr && *skip_if_nonzero != 0.f) return;
-    if (GUARDED) bc2_sqrt = clk->bc2_sqrt;
     float neg_step = 0.f;            // -(lr / bias_correction1) of this element's segment
 #pragma unroll 4
     for (int k = 0; k < segs.n; ++k)
-        if (i < segs.end[k]) { neg_step = GUARDED ? clk->neg_step[k] : segs.lr[k]; break; }
+        if (i < segs.end[k]) { neg_step = GUARDED ? s_neg[k] : segs.lr[k]; break; }
     const float gi = g[i];
     // torch.optim.Adam's math, op for op: lerp_(g, 1-b1); mul_(b2).addcmul_(g, g, 1-b2); sqrt / bc2_sqrt + eps; addcdiv_
     const float mi = fmaf(w1, gi - m[i], m[i]);
