@@ -175,7 +175,7 @@ def calc_ssim(img1, img2, window_size=11):
 
 
 def mapping_loss(params, frame, render, loss_weights=(0.5, 1.0), ignore_outlier_depth_loss=False, fused_loss=False,
-                 max_rendered=None):
+                 max_rendered=None, keep=None):
     """SplaTAM get_loss(mapping=True): Gaussians get gradient, camera does not
     (R/scripts/splatam.py:214-347 with tracking=False, mapping=True, do_ba=False, use_l1=True).
     frame: dict(im [3,H,W], depth [1,H,W], cam settings, w2c [4,4] first-frame w2c, id time index).
@@ -186,6 +186,9 @@ def mapping_loss(params, frame, render, loss_weights=(0.5, 1.0), ignore_outlier_
     else:
         tg = transform_to_frame(params, frame["id"], gaussians_grad=True, camera_grad=False)
         rv_rgb, rv_depth = rgb_rendervar(params, tg), depth_sil_rendervar(params, frame["w2c"], tg)
+    if keep is not None:       # the caller wants d loss / d means2D of the RGB render (densification statistic)
+        rv_rgb["means2D"].retain_grad()
+        keep["means2D"] = rv_rgb["means2D"]
     if fused_loss and render is default_render:      # N1: both colour sets in one raster pass
         from .rasterizer import GaussianRasterizer
         im, depth_sil, radius, _ = GaussianRasterizer(raster_settings=frame["cam"], max_rendered=max_rendered).forward_fused(
@@ -614,9 +617,82 @@ class ShardedMapper:
 
     def accumulate(self, frame):
         """Local backward of one keyframe into the flat gradient bucket (no communication)."""
-        loss, radius = mapping_loss(self.params(), frame, self.render, fused_loss=self.fused)
+        keep = {} if getattr(self, "track_means2D", False) else None
+        loss, radius = mapping_loss(self.params(), frame, self.render, fused_loss=self.fused, keep=keep)
         loss.backward()
+        if keep is not None:      # gradient of the RGB render's 2D means: the densification statistic (splatam.py:250)
+            self.last_means2D_grad = keep["means2D"].grad
         return loss.detach(), radius
+
+    # ---- gradient-based densification (3DGS-style; off in every shipped SLAM config) -----------------------------
+    def densify(self, iter, densify_dict, scene_radius, means2D_grad=None, seen=None, generator=None):
+        """densify of the reference (R/utils/slam_external.py:191-243), same schedule keys (start_after, stop_after,
+        densify_every, grad_thresh, num_to_split_into, removal_opacity_threshold, final_removal_opacity_threshold,
+        remove_big_after, reset_opacities, reset_opacities_every): accumulates |d loss / d means2D| of the seen
+        Gaussians, clones the small high-gradient ones, splits the large ones into num_to_split_into samples of
+        their own distribution, drops transparent / oversized ones and optionally resets opacities.  Parameters and both
+        Adam moments follow (new rows start with zero moments).  Every rank must call it with the same all-reduced
+        statistics; `generator` (default: the mapper's shared-seed generator when distributed, else torch's global
+        RNG, as the reference) draws the split samples.  Returns the Gaussian count afterwards."""
+        P = self.g.shapes["means3D"][0]
+        dev = self.g.flat.device
+        if not hasattr(self, "_dens") or self._dens["accum"].shape[0] != P:
+            self._dens = dict(accum=torch.zeros(P, device=dev), denom=torch.zeros(P, device=dev))
+        if iter > densify_dict["stop_after"]:
+            return P
+        means2D_grad = self.last_means2D_grad if means2D_grad is None else means2D_grad
+        seen = (self.g.seen_f > 0) if seen is None else seen
+        self._dens["accum"][seen] += torch.norm(means2D_grad[seen, :2], dim=-1)          # accumulate_mean2d_gradient
+        self._dens["denom"][seen] += 1
+        if not (iter >= densify_dict["start_after"] and iter % densify_dict["densify_every"] == 0):
+            return P
+        grads = self._dens["accum"] / self._dens["denom"]
+        grads[grads.isnan()] = 0.0
+        thr = densify_dict["grad_thresh"]
+        cur = lambda: {k: self.g.params[k].detach() for k in GAUSSIAN_KEYS}
+        big = lambda: torch.max(torch.exp(self.g.params["log_scales"].detach()), dim=1).values
+        to_clone = torch.logical_and(grads >= thr, big() <= 0.01 * scene_radius)
+        self.add_gaussians({k: v[to_clone] for k, v in cur().items()})
+        num = self.g.shapes["means3D"][0]
+        padded = torch.zeros(num, device=dev)
+        padded[:grads.shape[0]] = grads
+        to_split = torch.logical_and(padded >= thr, big() > 0.01 * scene_radius)
+        n = int(densify_dict["num_to_split_into"])
+        p = cur()
+        new = {k: v[to_split].repeat(n, 1) for k, v in p.items()}
+        stds = torch.exp(p["log_scales"])[to_split].repeat(n, 3)
+        if generator is None and self.world > 1:
+            generator = self._device_generator()
+        samples = torch.normal(mean=torch.zeros((stds.size(0), 3), device=dev), std=stds, generator=generator)
+        rots = build_rotation(p["unnorm_rotations"][to_split]).repeat(n, 1, 1)
+        new["means3D"] = new["means3D"] + torch.bmm(rots, samples.unsqueeze(-1)).squeeze(-1)
+        new["log_scales"] = torch.log(torch.exp(new["log_scales"]) / (0.8 * n))
+        self.add_gaussians(new)
+        self.remove_points(torch.cat((to_split, torch.zeros(n * int(to_split.sum()), dtype=torch.bool, device=dev))))
+        rthr = (densify_dict["final_removal_opacity_threshold"] if iter == densify_dict["stop_after"]
+                else densify_dict["removal_opacity_threshold"])
+        to_remove = (torch.sigmoid(self.g.params["logit_opacities"].detach()) < rthr).squeeze(-1)
+        if iter >= densify_dict["remove_big_after"]:
+            to_remove = torch.logical_or(to_remove, big() > 0.1 * scene_radius)
+        P = self.remove_points(to_remove)
+        self._dens = dict(accum=torch.zeros(P, device=dev), denom=torch.zeros(P, device=dev))
+        if iter > 0 and iter % densify_dict["reset_opacities_every"] == 0 and densify_dict["reset_opacities"]:
+            with torch.no_grad():
+                self.g.params["logit_opacities"].fill_(math.log(0.01 / 0.99))
+            if self.fused:
+                off = sum(math.prod(self.g.shapes[k]) for k in GAUSSIAN_KEYS[:3])
+                self.opt.m[off:off + P].zero_(); self.opt.v[off:off + P].zero_()
+            else:
+                st = self.opt.state.get(self.g.params["logit_opacities"], None)
+                if st:
+                    st["exp_avg"].zero_(); st["exp_avg_sq"].zero_()
+        return P
+
+    def _device_generator(self):
+        if getattr(self, "_dev_gen", None) is None:
+            self._dev_gen = torch.Generator(device=self.g.flat.device)
+            self._dev_gen.manual_seed(12345)
+        return self._dev_gen
 
     def step(self, window):
         """One sharded mapping step over `window` (list of keyframe dicts).  Returns the mean loss."""

@@ -219,3 +219,29 @@ def test_horn_aligned_ate_matches_reference():
         pkg.GaussianRasterizer, pkg.GaussianRasterizationSettings = object, object
         R = refsrc.load(pkg)
         assert abs(ours - float(R.eval_helpers.evaluate_ate(gt, est))) < 1e-6
+
+
+def test_densify_matches_reference():
+    """ShardedMapper.densify (torch path, CPU) == densify of R/utils/slam_external.py:191-243 on the fixture that the
+    reference's own function produced (tests/golden/host/make_golden_densify.py): parameters and both Adam moments
+    after an accumulate-only call and a clone + split + prune + opacity-reset call."""
+    import torch
+    from splatam_b200 import mapping as M
+    G = np.load(os.path.join(HERE, "golden", "host", "densify.npz"))
+    keys = M.GAUSSIAN_KEYS
+    init = {k: torch.from_numpy(G["init_" + k]) for k in keys}
+    m = M.ShardedMapper(init, torch.zeros(1, 4, 3), torch.zeros(1, 3, 3), lrs={k: 1e-3 for k in keys}, render=None, fused=False)
+    for k in keys:
+        m.g.params[k].grad.copy_(torch.from_numpy(G["grad_" + k]))
+    m.opt.step()
+    dd = eval(str(G["dict"][0]))
+    for call in (0, 1):
+        torch.manual_seed(70 + call)
+        P = m.densify(int(G["iter_%d" % call]), dd, float(G["scene_radius"]), means2D_grad=torch.from_numpy(G["m2d_%d" % call]),
+                      seen=torch.from_numpy(G["seen_%d" % call]))
+    assert P == G["out_means3D"].shape[0] != 300
+    for k in keys:
+        assert np.allclose(m.g.params[k].detach().numpy(), G["out_" + k], rtol=1e-6, atol=1e-7), k
+        st = m.opt.state[m.g.params[k]]
+        assert np.allclose(st["exp_avg"].numpy(), G["out_" + k + "_exp_avg"], rtol=1e-6, atol=1e-9), k
+        assert np.allclose(st["exp_avg_sq"].numpy(), G["out_" + k + "_exp_avg_sq"], rtol=1e-6, atol=1e-12), k

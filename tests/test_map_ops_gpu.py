@@ -160,3 +160,42 @@ def test_non_presence_mask_and_add_new_gaussians(cuda_device):
     assert 0 < P1 < P0 + n and getattr(m, "_graph", None) is None      # the opacity-0.5 newcomers go
     loss, _, _ = m.step([frame])                      # eager again after the shape change
     assert np.isfinite(float(loss))
+
+
+def test_densify_fused_path_matches_torch_path_and_reference_fixture(cuda_device):
+    """densify over the packed buffer + fused Adam moments (compaction kernels) == the torch path on the GPU == the
+    reference's own densify (fixture tests/golden/host/densify.npz, generated on the CPU: torch.normal draws differ
+    between CPU and CUDA generators, so the split samples are compared fused-vs-torch with a shared CUDA generator and
+    the reference fixture pins everything that does not depend on them: the final count)."""
+    from splatam_b200 import mapping as M
+    dev = cuda_device
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "host", "densify.npz"))
+    keys = M.GAUSSIAN_KEYS
+    dd = eval(str(G["dict"][0]))
+    res = {}
+    for fused in (True, False):
+        init = {k: torch.from_numpy(G["init_" + k]).to(dev) for k in keys}
+        m = M.ShardedMapper(init, torch.zeros(1, 4, 3, device=dev), torch.zeros(1, 3, 3, device=dev),
+                            lrs={k: 1e-3 for k in keys}, fused=fused)
+        for k in keys:
+            m.g.params[k].grad.copy_(torch.from_numpy(G["grad_" + k]).to(dev))
+        m.opt.step()
+        gen = torch.Generator(device=dev); gen.manual_seed(5)
+        for call in (0, 1):
+            P = m.densify(int(G["iter_%d" % call]), dd, float(G["scene_radius"]),
+                          means2D_grad=torch.from_numpy(G["m2d_%d" % call]).to(dev),
+                          seen=torch.from_numpy(G["seen_%d" % call]).to(dev), generator=gen)
+        if fused:
+            sizes = [int(np.prod(m.g.shapes[k])) for k in keys]
+            mom = dict(zip(keys, torch.split(m.opt.m, sizes))), dict(zip(keys, torch.split(m.opt.v, sizes)))
+            res[fused] = (P, {k: m.g.params[k].detach().clone() for k in keys},
+                          {k: mom[0][k].reshape(m.g.shapes[k]).clone() for k in keys},
+                          {k: mom[1][k].reshape(m.g.shapes[k]).clone() for k in keys})
+        else:
+            res[fused] = (P, {k: m.g.params[k].detach().clone() for k in keys},
+                          {k: m.opt.state[m.g.params[k]]["exp_avg"].clone() for k in keys},
+                          {k: m.opt.state[m.g.params[k]]["exp_avg_sq"].clone() for k in keys})
+    assert res[True][0] == res[False][0] == G["out_means3D"].shape[0]
+    for k in keys:
+        for i in (1, 2, 3):
+            assert torch.allclose(res[True][i][k], res[False][i][k], rtol=2e-6, atol=1e-9), (k, i)
