@@ -19,7 +19,8 @@ BASE = {"metric": str, "value": float, "unit": str, "n_gpus": int, "steps": int,
 
 
 @pytest.mark.parametrize("name", ["r01_bench_ours_final.json", "r01_bench_reference_final.json",
-                                  "r01_bench_ours_final_2gpu.json"])
+                                  "r01_bench_ours_final_2gpu.json", "r02_bench_ours_final.json",
+                                  "r02_bench_reference_final.json", "r02_bench_ours_8gpu_midround.json"])
 def test_bench_line_has_the_contract_keys(name):
     d = _line(name)
     for k, t in BASE.items():
@@ -52,3 +53,23 @@ def test_ours_line_counts_its_own_kernels_and_reference_line_is_tagged():
     # the headline claims of DESIGN.md section 5
     assert ours["value"] / ref["value"] > 2.0 and ours["e2e"]["value"] / ref["e2e"]["value"] > 2.0
     assert ours["mapping"]["value"] / ref["mapping"]["value"] > 6.0
+
+
+def test_round2_lines():
+    """Round-2 additions: own-kernel launch count incl. the radix sort, the eager drop-in number, traffic read from the
+    committed ncu capture, the mapping line on the view-filling map with the stock reference loop."""
+    ours, ref = _line("r02_bench_ours_final.json"), _line("r02_bench_reference_final.json")
+    assert ours["gpu_launches"] == 16 * ours["steps"] and ref["impl"] == "reference"
+    assert ours["config"]["num_rendered"] == ref["config"]["num_rendered"] == 3097789
+    assert ours["value"] / ref["value"] > 3.0 and ours["e2e"]["value"] / ref["e2e"]["value"] > 2.5
+    assert ours["eager_drop_in"]["value"] / ref["value"] > 2.0
+    assert len(ours["e2e"]["runs_ms_per_step"]) == 3
+    rf = ours["roofline"]
+    traffic = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))["ours"][rf["kernel"]]["dram_bytes"]
+    assert rf["kernel"] == "blend_backward" and rf["traffic"] == traffic > rf["algorithmic_bytes_per_launch"]
+    mo, mr = ours["mapping"], ref["mapping"]
+    assert mo["workload"] == mr["workload"] == "view_filling_1000000" and mo["steps"] >= 50
+    assert mo["num_rendered"] > 1.5 * mo["visible"] and mo["visible"] > 0.99 * mo["gaussians"]
+    assert "stock get_loss" in mr["impl_note"] and mo["value"] / mr["value"] > 6.0
+    m8 = _line("r02_bench_ours_8gpu_midround.json")["mapping"]
+    assert m8["keyframes_per_step"] == 8 and m8["allreduce_ms"] > 0 and m8["value"] > 6.0 * 456.0
