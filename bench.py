@@ -476,6 +476,77 @@ def mapping_bench(dev, world, dist_on, impl, steps=50, warmup=5, P=1_000_000):
                      gaussians=P, width=sc.w, height=sc.h, workload=sc.name), **out)
 
 
+def tracking_bench(dev, impl, iters=40, P=50_000):
+    """BASELINE config[1]: the tracking-only inner loop (camera-only Adam, silhouette-masked L1 sums, 40 iterations per
+    frame: R/configs/replica/splatam.py:59-80) on a ~50k-Gaussian map that covers a 1200x680 view.
+    ours: mapping.track_frame over the fused path (fused glue with the pose gradient, two-set render, fused masked L1).
+    reference: the STOCK loop of R/scripts/splatam.py:690-738 -- unmodified get_loss(tracking=True) +
+    initialize_optimizer(tracking=True) over the unmodified reference extension.  Single GPU (tracking does not shard)."""
+    Rast, Settings = get_ops(impl)
+    sc = scenes.view_filling(seed=12, P=P, cover=True, opacity=(0.85, 0.95))
+    cam = sc.settings(Settings, dev)
+    gauss = dict(means3D=sc.means3D, rgb_colors=sc.colors, unnorm_rotations=sc.rotations,
+                 logit_opacities=torch.logit(sc.opacities.clamp(0.02, 0.98)), log_scales=torch.log(sc.scales[:, :1]))
+    gauss = {k: v.to(dev).contiguous() for k, v in gauss.items()}
+    from splatam_b200 import slam, mapping as M
+    rots, trans = slam.look_trajectory(2, dev)
+    render = None if impl == "ours" else (lambda settings, **rv: Rast(raster_settings=settings)(**rv))
+    target = slam.render_frame(gauss, rots, trans, 1, cam, render)
+    target["depth"] = torch.where(target["sil"] > 0.9, target["depth"] / target["sil"].clamp(min=1e-6), torch.zeros_like(target["depth"]))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def fresh_pose():
+        r = torch.zeros(1, 4, 2, device=dev); r[:, 0] = 1.0
+        return r, torch.zeros(1, 3, 2, device=dev)
+    if impl == "ours":
+        def run():
+            r, t = fresh_pose()
+            p = dict({k: v.detach() for k, v in gauss.items()}, cam_unnorm_rots=r, cam_trans=t)
+            # graph=True: a tracking-only run over a map that stays put re-uses one captured iteration frame after frame
+            return M.track_frame(p, target, num_iters=iters, fused=True, graph=True)
+    else:
+        import refsrc
+        if not refsrc.available():
+            return {"unavailable": "reference Python (baseline/_ref/SplaTAM) not installed"}
+        R = refsrc.load(reference_extension())
+        lrs = dict(means3D=0.0, rgb_colors=0.0, unnorm_rotations=0.0, logit_opacities=0.0, log_scales=0.0,
+                   cam_unnorm_rots=0.0004, cam_trans=0.002)               # R/configs/replica/splatam.py:71-79
+        data = dict(cam=cam, im=target["im"], depth=target["depth"], id=1, intrinsics=None, w2c=torch.eye(4, device=dev),
+                    iter_gt_w2c_list=None)
+
+        def run():
+            r, t = fresh_pose()
+            params = {k: torch.nn.Parameter(v.clone().contiguous()) for k, v in dict(gauss, cam_unnorm_rots=r, cam_trans=t).items()}
+            variables = dict(max_2D_radius=torch.zeros(sc.P, device=dev), means2D_gradient_accum=torch.zeros(sc.P, device=dev),
+                             denom=torch.zeros(sc.P, device=dev))
+            opt = R.splatam.initialize_optimizer(params, lrs, tracking=True)
+            best, losses = float(1e20), []
+            for _ in range(iters):                                        # splatam.py:690-712
+                loss, variables, _ = R.splatam.get_loss(params, data, variables, 1, dict(im=0.5, depth=1.0), True, 0.99, True,
+                                                        False, tracking=True)
+                loss.backward()
+                opt.step()
+                opt.zero_grad(set_to_none=True)
+                with torch.no_grad():
+                    if loss < best:
+                        best = loss
+                        cand = (params["cam_unnorm_rots"][..., 1].detach().clone(), params["cam_trans"][..., 1].detach().clone())
+                losses.append(float(loss))
+            return losses
+    run()                                                                # warm-up frame
+    torch.cuda.synchronize(dev)
+    e0.record()
+    losses = run()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / iters
+    return dict(metric="tracking iters/sec", value=1000.0 / ms, unit="iters/s", ms_per_iter=ms, iters=iters, gaussians=sc.P,
+                width=sc.w, height=sc.h, workload=sc.name, first_loss=losses[0], last_loss=losses[-1],
+                note="config 2: tracking-only inner loop on a 50k-Gaussian view-covering map; " +
+                     ("fused path (mapping.track_frame)" if impl == "ours" else
+                      "stock get_loss(tracking=True) + initialize_optimizer(tracking=True), reference extension"))
+
+
 def cpu_oracle_run(scene, budget_s=25.0):
     """Times the C oracle (fwd render OpenMP over tiles, backward single-threaded double accumulation)
     on a bounded sample: the same view with the first P_s Gaussians, P_s chosen so one fwd+bwd stays
@@ -680,6 +751,10 @@ def main():
             line["mapping"] = mapping_bench(dev, world, dist_on, args.impl)
         except Exception as e:  # never lose the headline line
             line["mapping"] = {"error": repr(e)[:200]}
+        try:
+            line["tracking"] = tracking_bench(dev, args.impl)
+        except Exception as e:
+            line["tracking"] = {"error": repr(e)[:200]}
     if rank == 0:
         print(json.dumps(line))
     if dist_on:

@@ -251,13 +251,24 @@ def tracking_loss(params, frame, render, sil_thres=0.99, loss_weights=(0.5, 1.0)
     return loss_weights[0] * l_im + loss_weights[1] * l_depth, radius
 
 
-def track_frame(params, frame, render=None, num_iters=40, lr_rot=0.0004, lr_trans=0.002, fused=None):
+def track_frame(params, frame, render=None, num_iters=40, lr_rot=0.0004, lr_trans=0.002, fused=None, graph=None):
     """SplaTAM's tracking inner loop for one frame (R/scripts/splatam.py:676-744): Adam on the frame's camera
     quaternion and translation only, keeping the best-loss pose.  `params` holds detached Gaussian tensors and
-    cam_unnorm_rots [1,4,T] / cam_trans [1,3,T] leaf tensors.  Returns the list of per-iteration losses."""
+    cam_unnorm_rots [1,4,T] / cam_trans [1,3,T] leaf tensors.  Returns the list of per-iteration losses.
+    graph: the iteration -- loss forward + backward over the sync-free rasterizer, the Adam step and the best-pose
+    bookkeeping, all on the device -- is captured once and replayed, so a frame costs one host synchronisation instead of
+    one per iteration (`_TrackingGraph`); None = re-use a cached graph, build one only for loops of >= 100 iterations."""
     render = default_render if render is None else render
     if fused is None:
         fused = params["means3D"].is_cuda and render is default_render
+    can_graph = bool(fused) and params["means3D"].is_cuda and render is default_render
+    if can_graph and graph is not False:
+        # default policy: always re-use a cached graph; BUILD one only where it pays -- long loops (TUM: 200 iterations
+        # per frame) or on request (graph=True: tracking-only runs over a map that stays put).  Building costs about as
+        # much as ~40 eager iterations (capacity probe, warm-up, capture into a fresh memory pool).
+        out = _track_frame_graphed(params, frame, num_iters, lr_rot, lr_trans, build=(graph is True or num_iters >= 100))
+        if out is not None:
+            return out              # None: no graph, or the instance capacity overflowed mid-frame -> run eagerly
     rots, trans = params["cam_unnorm_rots"], params["cam_trans"]
     rots.requires_grad_(True); trans.requires_grad_(True)
     opt = torch.optim.Adam([{"params": [rots], "lr": lr_rot}, {"params": [trans], "lr": lr_trans}], lr=0.0, eps=1e-15)
@@ -279,6 +290,144 @@ def track_frame(params, frame, render=None, num_iters=40, lr_rot=0.0004, lr_tran
         rots[..., t] = best_rot
         trans[..., t] = best_tran
     return losses
+
+
+def _capture(body):
+    """Captures body() on the CURRENT (non-default) stream into a CUDA graph.  capture_begin / capture_end directly: the
+    torch.cuda.graph context manager also runs gc.collect() and torch.cuda.empty_cache(), which costs tens of
+    milliseconds and throws the allocator's cached blocks away."""
+    g = torch.cuda.CUDAGraph()
+    g.capture_begin()
+    try:
+        body()
+    finally:
+        g.capture_end()
+    return g
+
+
+class _TrackingGraph:
+    """One captured tracking iteration (loss forward + backward over the sync-free rasterizer, capturable Adam step,
+    best-pose bookkeeping, all on the device) bound to ONE map (the parameter tensors' storage), camera and iteration
+    count -- not to a pose column: the pose travels through two small leaf tensors.  Re-used frame after frame while the map tensors stay the same objects (tracking-only runs; SLAM phases
+    without map growth): a frame then costs two small image copies, `num_iters` graph launches and one host
+    synchronisation."""
+
+    def __init__(self, params, frame, num_iters, lr_rot, lr_trans, slack=1.5):
+        from .rasterizer import GaussianRasterizer
+        from .train_ops import masked_l1
+        dev = params["means3D"].device
+        self.dev, self.t, self.num_iters = dev, frame["id"], num_iters
+        t = frame["id"]
+        rots, trans = params["cam_unnorm_rots"], params["cam_trans"]
+        self.gp = dict({k: params[k].detach() for k in GAUSSIAN_KEYS}, cam_unnorm_rots=rots.detach(), cam_trans=trans.detach())
+        self.key = _tracking_key(params, frame, num_iters)
+        gp = self.gp
+        with torch.no_grad():       # one synchronous forward at the starting pose sizes the capacity
+            rgb, _ = fused_rendervars(gp, t, frame["w2c"], camera_grad=False, pose=pose_matrices(gp, t))
+            GaussianRasterizer(frame["cam"])(means3D=rgb["means3D"], means2D=rgb["means2D"], opacities=rgb["opacities"],
+                                             colors_precomp=rgb["colors_precomp"], scales=rgb["scales"],
+                                             rotations=rgb["rotations"])
+        cap = int(_last_num_rendered() * slack) + 4096
+        self.side = torch.cuda.Stream(dev)
+        self.side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(self.side):
+            self.im, self.depth, self.w2c = frame["im"].clone(), frame["depth"].clone(), frame["w2c"].clone()
+            self.q = rots[..., t].detach().clone().requires_grad_(True)      # [1,4], [1,3]: leaves born on the capture stream
+            self.tr = trans[..., t].detach().clone().requires_grad_(True)
+            q, tr = self.q, self.tr
+            q.grad, tr.grad = torch.zeros_like(q), torch.zeros_like(tr)
+            self.opt = torch.optim.Adam([{"params": [q], "lr": lr_rot}, {"params": [tr], "lr": lr_trans}], lr=0.0,
+                                        eps=1e-15, capturable=True)
+            self.best_loss = torch.full((), float("inf"), device=dev)
+            self.best_q, self.best_tr = q.detach().clone(), tr.detach().clone()
+            self.hist = torch.zeros(num_iters, device=dev)
+            self.it = torch.zeros(1, dtype=torch.long, device=dev)
+            self.bad_any = torch.zeros(1, device=dev)
+            cam = frame["cam"]
+
+            def body():
+                q.grad.zero_(); tr.grad.zero_()
+                cam_rot = F.normalize(q)
+                rel = torch.eye(4, device=dev, dtype=torch.float32)
+                rel[:3, :3] = build_rotation(cam_rot)
+                rel[:3, 3] = tr
+                rgb, dep = fused_rendervars(gp, t, self.w2c, camera_grad=True, pose=(rel, cam_rot))
+                im, depth_sil, _, _ = GaussianRasterizer(cam, max_rendered=cap).forward_fused(
+                    means3D=rgb["means3D"], means2D=rgb["means2D"], opacities=rgb["opacities"],
+                    colors_precomp=rgb["colors_precomp"], colors_extra=dep["colors_precomp"], scales=rgb["scales"],
+                    rotations=rgb["rotations"])
+                l_depth, l_im = masked_l1(depth_sil, self.depth, im, self.im, sil_thres=0.99, use_sil=True, depth_mean=False)
+                loss = 0.5 * l_im + 1.0 * l_depth
+                loss.backward()
+                lossd = loss.detach().reshape(1)
+                bad = (GaussianRasterizer.last_state(dev).header()[2:3] != 0) | ~torch.isfinite(lossd)
+                q.grad.copy_(torch.where(bad, torch.zeros_like(q.grad), q.grad))
+                tr.grad.copy_(torch.where(bad, torch.zeros_like(tr.grad), tr.grad))
+                self.bad_any.add_(bad.float())
+                self.opt.step()
+                # the reference's rule (splatam.py:703-712): candidate = pose AFTER the step, ranked by the loss evaluated
+                # before it; the first strictly smaller loss wins
+                better = (lossd < self.best_loss) & ~bad
+                self.best_loss.copy_(torch.where(better, lossd, self.best_loss.reshape(1)).reshape(()))
+                self.best_q.copy_(torch.where(better, q.detach(), self.best_q))
+                self.best_tr.copy_(torch.where(better, tr.detach(), self.best_tr))
+                self.hist.scatter_(0, self.it, lossd)
+                self.it.add_(1)
+            self.body = body
+            for _ in range(3):              # warm-up (initialises the capturable Adam state); undone by reset()
+                body()
+            self.graph = _capture(body)
+        torch.cuda.current_stream(dev).wait_stream(self.side)
+
+    def reset(self, params, frame):
+        """Loads a frame: images, starting pose, fresh optimizer state (the reference builds a new Adam per frame,
+        splatam.py:680), empty best-pose record."""
+        t = frame["id"]
+        with torch.no_grad():
+            self.im.copy_(frame["im"]); self.depth.copy_(frame["depth"]); self.w2c.copy_(frame["w2c"])
+            self.q.copy_(params["cam_unnorm_rots"][..., t]); self.tr.copy_(params["cam_trans"][..., t])
+            for st in self.opt.state.values():
+                st["exp_avg"].zero_(); st["exp_avg_sq"].zero_(); st["step"].zero_()
+            self.best_loss.fill_(float("inf")); self.best_q.copy_(self.q); self.best_tr.copy_(self.tr)
+            self.hist.zero_(); self.it.zero_(); self.bad_any.zero_()
+
+    def run(self, params, frame):
+        dev = self.dev
+        self.side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(self.side):
+            self.reset(params, frame)
+            for _ in range(self.num_iters):
+                self.graph.replay()
+        torch.cuda.current_stream(dev).wait_stream(self.side)
+        if float(self.bad_any) != 0.0:                                   # the one host synchronisation of the frame
+            return None
+        with torch.no_grad():
+            params["cam_unnorm_rots"][..., frame["id"]] = self.best_q
+            params["cam_trans"][..., frame["id"]] = self.best_tr
+        return self.hist.tolist()
+
+
+_TRACK_GRAPHS = {}
+
+
+def _tracking_key(params, frame, num_iters):
+    return (params["means3D"].data_ptr(), tuple(params["means3D"].shape), params["log_scales"].shape[1],
+            id(frame["cam"]), tuple(frame["im"].shape), num_iters)
+
+
+def _track_frame_graphed(params, frame, num_iters, lr_rot, lr_trans, build=True):
+    """Graph-replayed tracking of one frame, or None when no graph is available / an iteration overflowed the instance
+    capacity (the caller then runs the frame eagerly).  Graphs are cached per (map storage, camera, pose column,
+    iteration count); `build` creates one on a miss (worth it for long loops or when the map stays put)."""
+    key = _tracking_key(params, frame, num_iters)
+    tg = _TRACK_GRAPHS.get(key)
+    if tg is None:
+        if not build:
+            return None
+        if len(_TRACK_GRAPHS) >= 2:
+            _TRACK_GRAPHS.clear()
+        tg = _TRACK_GRAPHS[key] = _TrackingGraph(params, frame, num_iters, lr_rot, lr_trans)
+    return tg.run(params, frame)
 
 
 class FlatGaussians:
@@ -523,7 +672,9 @@ class ShardedMapper:
         f0 = window[0]
         if capacity is None:
             worst = 0
-            for fr in window:            # one synchronous pass to size the capacity
+            probe = window if len(window) <= 3 else [window[0], window[len(window) // 2], window[-1]]
+            for fr in probe:             # a few synchronous forwards size the capacity (an overflow later is safe: it
+                                         # skips the step and re-captures, see the docstring)
                 with torch.no_grad():
                     rgb, dep = fused_rendervars(self.params(), fr["id"], fr["w2c"], camera_grad=False)
                     c, _, _ = GaussianRasterizer(fr["cam"])(**rgb)
@@ -543,15 +694,16 @@ class ShardedMapper:
                 self.g.zero_grad()
                 loss, radius = mapping_loss(self.params(), self._static, self.render, fused_loss=True, max_rendered=self._cap)
                 loss.backward()
-        torch.cuda.current_stream(dev).wait_stream(side)
-        self._graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self._graph):
+        def body():
             self.g.bucket.zero_()
             loss, radius = mapping_loss(self.params(), self._static, self.render, fused_loss=True, max_rendered=self._cap)
             loss.backward()
             self.g.seen_f.copy_(radius > 0)
             self.g.loss_slot.copy_(loss.detach().reshape(1))
             self.g.overflow_slot.copy_(GaussianRasterizer.last_state(dev).header()[2:3])     # int32 0/1 -> float
+        with torch.cuda.stream(side):
+            self._graph = _capture(body)
+        torch.cuda.current_stream(dev).wait_stream(side)
         return self._cap
 
     def _replay(self, frame):
