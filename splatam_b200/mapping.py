@@ -490,6 +490,10 @@ class ShardedMapper:
         self.render = render
         self.gen = torch.Generator().manual_seed(seed)   # shared seed -> identical schedule on every rank
         self.step_idx = 0
+        # graph mode, world > 1: the bucket is all-reduced in this many slices, the guarded Adam update of slice k
+        # overlapping the transfer of slice k+1 (1 = one collective, then one Adam launch)
+        import os as _os
+        self.overlap_chunks = int(_os.environ.get("SPLATAM_OVERLAP_CHUNKS", "2"))
 
     def params(self):
         return dict(self.g.params, **self.cam)
@@ -858,11 +862,30 @@ class ShardedMapper:
             loss, radius = self.accumulate(window[picks[self.rank]])
             self.g.seen_f.copy_(radius > 0)
             self.g.loss_slot.copy_(loss.reshape(1))
-        if self.dist and self.world > 1:
+        chunked = graphed and self.dist is not None and self.world > 1 and self.overlap_chunks > 1
+        if chunked:
+            # The bucket travels as K slices, the TAIL first (it carries the seen flags, the loss and the overflow flag
+            # that every later Adam chunk needs); the guarded Adam update of slice k runs on the compute stream as soon as
+            # its all-reduce has landed, while NCCL moves slice k+1: only the last slice's update is exposed.
+            n = self.g.flat.numel()
+            K = int(self.overlap_chunks)
+            cuts = [n * i // K for i in range(K)] + [n]
+            works = [self.dist.all_reduce(self.g.bucket[cuts[K - 1]:], op=self.dist.ReduceOp.SUM, group=self.group,
+                                          async_op=True)]
+            works += [self.dist.all_reduce(self.g.bucket[cuts[i]:cuts[i + 1]], op=self.dist.ReduceOp.SUM, group=self.group,
+                                           async_op=True) for i in range(K - 1)]
+            works[0].wait()
+            self.opt.advance_clock(self.g.overflow_slot)
+            self.opt.apply_range(cuts[K - 1], n - cuts[K - 1], self.g.overflow_slot)
+            for i in range(K - 1):
+                works[i + 1].wait()
+                self.opt.apply_range(cuts[i], cuts[i + 1] - cuts[i], self.g.overflow_slot)
+        elif self.dist and self.world > 1:
             # ONE collective per step: gradients, seen flags (sum of 0/1 > 0 == OR) and the loss travel together
             self.dist.all_reduce(self.g.bucket, op=self.dist.ReduceOp.SUM, group=self.group)
         if graphed:
-            self.opt.step_guarded(self.g.overflow_slot)        # no-op on every rank if any rank's render overflowed
+            if not chunked:
+                self.opt.step_guarded(self.g.overflow_slot)    # no-op on every rank if any rank's render overflowed
             host = self._pin[self.step_idx % len(self._pin)]
             host.copy_(self.g.overflow_slot, non_blocking=True)
             ev = torch.cuda.Event()
