@@ -493,7 +493,7 @@ class ShardedMapper:
         # graph mode, world > 1: the bucket is all-reduced in this many slices, the guarded Adam update of slice k
         # overlapping the transfer of slice k+1 (1 = one collective, then one Adam launch)
         import os as _os
-        self.overlap_chunks = int(_os.environ.get("SPLATAM_OVERLAP_CHUNKS", "2"))
+        self.overlap_chunks = int(_os.environ.get("SPLATAM_OVERLAP_CHUNKS", "1"))
 
     def params(self):
         return dict(self.g.params, **self.cam)
