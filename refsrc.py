@@ -138,8 +138,18 @@ def install(dst=None):
     dst = dst or _CANDIDATES[1]
     if not os.path.isdir(os.path.join(src, "utils")):
         return os.path.isdir(os.path.join(dst, "utils"))
+    def _writable(func, path, _exc):          # the source tree is read-only and copytree keeps its modes
+        os.chmod(path, 0o755)
+        func(path)
     for sub in ("utils", "scripts", "configs", os.path.join("datasets", "gradslam_datasets")):
         d = os.path.join(dst, sub)
-        shutil.rmtree(d, ignore_errors=True)
+        if os.path.isdir(d):
+            for root, dirs, files in os.walk(d):
+                os.chmod(root, 0o755)
+            shutil.rmtree(d, onerror=_writable)
         shutil.copytree(os.path.join(src, sub), d)
+        for root, dirs, files in os.walk(d):          # keep the install removable / re-installable
+            os.chmod(root, 0o755)
+            for f in files:
+                os.chmod(os.path.join(root, f), 0o644)
     return True

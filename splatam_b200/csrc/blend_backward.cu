@@ -19,8 +19,8 @@
 //                               the colour seen behind the Gaussian (as a scalar: only its dot product with
 //                               dL/dpixel is ever used), dL/dalpha -> w = G dL/dG and ca = alpha T, written
 //                               back into the matrix.  A lane never spends an iteration on a Gaussian that
-//                               does not cover its pixel: 2.0x fewer iterations than a warp-lock-stepped walk
-//                               on the 1M-Gaussian bench (tools/lane_packing_model.py);
+//                               does not cover its pixel: 1.8-2.0x fewer iterations than a warp-lock-stepped walk
+//                               on the 1M-Gaussian bench (tools/lane_window_model.py);
 //   reduce   (lane = Gaussian, two lanes per slot): sweep the slot's 32 pixels, accumulate the nine moment
 //                               sums in registers at full lane utilisation, and flush them with three
 //                               16-byte vector reductions (REDG.E.ADD.F32x4) per (warp, Gaussian).
