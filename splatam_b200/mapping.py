@@ -778,6 +778,7 @@ class ShardedMapper:
         loss.backward()
         if keep is not None:      # gradient of the RGB render's 2D means: the densification statistic (splatam.py:250)
             self.last_means2D_grad = keep["means2D"].grad
+            self.last_seen_local = (radius > 0)
         return loss.detach(), radius
 
     # ---- gradient-based densification (3DGS-style; off in every shipped SLAM config) -----------------------------
@@ -797,9 +798,19 @@ class ShardedMapper:
         if iter > densify_dict["stop_after"]:
             return P
         means2D_grad = self.last_means2D_grad if means2D_grad is None else means2D_grad
-        seen = (self.g.seen_f > 0) if seen is None else seen
-        self._dens["accum"][seen] += torch.norm(means2D_grad[seen, :2], dim=-1)          # accumulate_mean2d_gradient
-        self._dens["denom"][seen] += 1
+        if seen is None:       # the Gaussians THIS rank's render saw (the bucket's seen flags are already summed over ranks)
+            seen = self.last_seen_local if getattr(self, "last_seen_local", None) is not None else (self.g.seen_f > 0)
+        if self.dist and self.world > 1:
+            # K ranks rendered K keyframes this step: the statistic of the step is the sum over the keyframes, exactly
+            # what K sequential single-keyframe steps of the reference would have accumulated; summing it over the ranks
+            # also keeps the replicas' clone / split decisions identical
+            st = torch.stack([torch.norm(means2D_grad[:, :2], dim=-1) * seen, seen.to(torch.float32)])
+            self.dist.all_reduce(st, op=self.dist.ReduceOp.SUM, group=self.group)
+            self._dens["accum"] += st[0]
+            self._dens["denom"] += st[1]
+        else:
+            self._dens["accum"][seen] += torch.norm(means2D_grad[seen, :2], dim=-1)      # accumulate_mean2d_gradient
+            self._dens["denom"][seen] += 1
         if not (iter >= densify_dict["start_after"] and iter % densify_dict["densify_every"] == 0):
             return P
         grads = self._dens["accum"] / self._dens["denom"]

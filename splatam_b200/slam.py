@@ -65,7 +65,7 @@ def _curr_w2c(rots, trans, t):
 def run_slam(gauss_init, frames, cam, render=None, tracking_iters=20, mapping_iters=8, keyframe_every=2,
              window=4, fused=None, seed=0, intrinsics=None, add_new_gaussians=False, sil_thres=0.5, prune_dict=None,
              scene_radius=None, select_keyframes=False, checkpoint_dir=None, first_frame_iters=0, map_every=None,
-             graph=False, timing=None):
+             graph=False, timing=None, densify_dict=None):
     """Tracks every frame and maps on keyframes.  gauss_init: dict of the five Gaussian tensors (the map's
     starting point); frames: list of dict(id, cam, w2c, im, depth).  Returns dict(rots, trans, psnr, gauss).
 
@@ -77,7 +77,9 @@ def run_slam(gauss_init, frames, cam, render=None, tracking_iters=20, mapping_it
     iterations run on frame 0 before tracking starts (needed when the map is a raw back-projection).
     `map_every` (default: keyframe_every) maps every map_every-th frame while only every keyframe_every-th frame joins
     the keyframe list, as the reference's two config keys do (splatam.py:777,912).  `graph`: each mapping phase is
-    captured into a CUDA graph over the sync-free rasterizer (fused path only).  `timing`: dict that receives the
+    captured into a CUDA graph over the sync-free rasterizer (fused path only).  `densify_dict`: gradient-based
+    densification inside the mapping iterations (the reference's `use_gaussian_splatting_densification` branch,
+    splatam.py:863-864; eager steps only -- the map size changes).  `timing`: dict that receives the
     accumulated wall seconds of tracking / mapping (synchronised) and the mapping iteration count."""
     import time
     map_every = keyframe_every if map_every is None else map_every
@@ -89,6 +91,7 @@ def run_slam(gauss_init, frames, cam, render=None, tracking_iters=20, mapping_it
     trans = torch.zeros(1, 3, T, device=dev)
     kw = {} if render is None else {"render": render}
     mapper = M.ShardedMapper(gauss_init, rots, trans, seed=seed, fused=fused, **kw)
+    mapper.track_means2D = densify_dict is not None
     keyframes = [dict(frames[0], est_w2c=torch.eye(4, device=dev))]
     counts = [mapper.g.shapes["means3D"][0]]
     for it in range(first_frame_iters):       # the reference maps frame 0 before it tracks frame 1 (splatam.py:777)
@@ -130,7 +133,7 @@ def run_slam(gauss_init, frames, cam, render=None, tracking_iters=20, mapping_it
             else:
                 win = (keyframes + [cur])[-window:]
             mapper.reset_optimizer()                          # splatam.py:822
-            if graph:
+            if graph and densify_dict is None:
                 mapper.enable_graph(win)
             torch.cuda.synchronize(dev) if dev.type == "cuda" else None
             t0 = time.perf_counter()
@@ -138,6 +141,8 @@ def run_slam(gauss_init, frames, cam, render=None, tracking_iters=20, mapping_it
                 mapper.step(win)
                 if prune_dict is not None:
                     mapper.prune_gaussians(it, prune_dict, scene_radius)
+                if densify_dict is not None:
+                    mapper.densify(it, densify_dict, scene_radius)
             if graph and getattr(mapper, "_graph", None) is not None:
                 mapper._poll_overflow(win, block=True)
             torch.cuda.synchronize(dev) if dev.type == "cuda" else None

@@ -158,3 +158,38 @@ def test_single_rank_results_are_broadcast():
         assert (a == b).all()
     assert (res[1][1] == rots.numpy()).all() and (res[1][2] == trans.numpy()).all()
     assert (res[1][3] == frames[0]["im"].numpy()).all() and (res[1][5] == torch.eye(4).numpy()).all()
+
+
+def _worker_densify(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(2)
+    gauss, rots, trans, frames = _problem()
+    mapper = M.ShardedMapper(gauss, rots, trans, render=_cpu_render, seed=77)
+    mapper.track_means2D = True
+    dd = dict(start_after=0, remove_big_after=0, stop_after=10, densify_every=1, grad_thresh=1e-9, num_to_split_into=2,
+              removal_opacity_threshold=0.05, final_removal_opacity_threshold=0.05, reset_opacities=False,
+              reset_opacities_every=100)
+    counts = []
+    for it in range(2):
+        mapper.step(frames)                                   # each rank renders a different keyframe
+        counts.append(mapper.densify(it, dd, scene_radius=0.4))
+    loss, _, _ = mapper.step(frames)                          # the resized replicas keep stepping together
+    q.put((rank, counts, mapper.g.flat.detach().numpy().copy(), loss))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_densify_keeps_replicas_identical():
+    """Gradient-based densification on two ranks: the statistic is summed over the ranks' keyframes and the split samples
+    come from a shared-seed generator, so both replicas clone / split / prune identically."""
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_densify, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = sorted([q.get(timeout=300) for _ in range(2)], key=lambda t: t[0])
+    [p.join(60) for p in procs]
+    (_, ca, fa, la), (_, cb, fb, lb) = res
+    assert ca == cb and ca[-1] != 96
+    assert fa.shape == fb.shape and (fa == fb).all() and abs(la - lb) < 1e-7

@@ -44,3 +44,27 @@ def test_slam_loop_host_logic(tmp_path):
     assert ck["means3D"].shape[0] == out["counts"][-1] and ck["cam_unnorm_rots"].shape == (1, 4, T)
     assert (tmp_path / "params2.npz").exists()
     assert slam.ate_rmse(rots, trans, rots, trans) == 0.0 and slam.psnr(frames[0]["im"], frames[0]["im"] * 0 + 0.5) > 0
+
+
+def test_slam_loop_with_gradient_densification(tmp_path):
+    """The reference's optional densification branch inside the mapping iterations (splatam.py:863-864): the map is
+    cloned / split by the 2D-mean gradient statistic and pruned, the loop carries on with the resized map."""
+    import splatam_b200 as S
+    torch.set_num_threads(4)
+    sc = scenes.config1(seed=8, P=120, w=48, h=32)
+    cam = sc.settings(S.GaussianRasterizationSettings, "cpu")
+    gt = dict(means3D=sc.means3D, rgb_colors=sc.colors, unnorm_rotations=sc.rotations,
+              logit_opacities=torch.logit(sc.opacities.clamp(0.05, 0.95)), log_scales=torch.log(sc.scales[:, :1]))
+    T = 3
+    rots, trans = slam.look_trajectory(T, "cpu", step=(0.004, -0.002, 0.003), rot_step=(0.001, -0.001, 0.0005))
+    frames = [slam.render_frame(gt, rots, trans, t, cam, render=_cpu_render) for t in range(T)]
+    init = dict(gt)
+    init["rgb_colors"] = (gt["rgb_colors"] + 0.2).clamp(0, 1)          # a wrong map: non-zero gradients everywhere
+    dd = dict(start_after=0, remove_big_after=0, stop_after=10, densify_every=1, grad_thresh=1e-7, num_to_split_into=2,
+              removal_opacity_threshold=0.02, final_removal_opacity_threshold=0.02, reset_opacities=False,
+              reset_opacities_every=100)
+    torch.manual_seed(2); np.random.seed(2)
+    out = slam.run_slam(init, frames, cam, render=_cpu_render, fused=False, tracking_iters=2, mapping_iters=2,
+                        keyframe_every=1, window=2, scene_radius=0.5, densify_dict=dd)
+    assert out["counts"][-1] != 120 and torch.isfinite(out["gauss"]["means3D"]).all() and np.isfinite(out["psnr"])
+    assert out["gauss"]["means3D"].shape[0] == out["counts"][-1] == out["gauss"]["logit_opacities"].shape[0]
