@@ -138,3 +138,19 @@ def test_oracle_matches_reference_golden(path):
     for k in ["means3D", "means2D", "colors", "opacities", "scales", "rotations"]:
         ref = z["ref_grad_" + k].reshape(-1)
         assert l2_rel(g[k].reshape(-1), ref) < 1e-4, (k, l2_rel(g[k].reshape(-1), ref))
+
+
+def test_view_filling_workloads_are_representative():
+    """The benchmark maps that stand for SplaTAM's own (scenes.view_filling) put EVERY Gaussian in view and give
+    num_rendered >= 1.5 x P, unlike round 1's `room` scenes where ~97 % of the Gaussians lay outside the frustum
+    (checked with the C oracle's projection + tile count, which is bit-identical to the reference's)."""
+    import scenes
+    for sc, lo, hi in [(scenes.view_filling(seed=12), 2.0, 2.6),                                  # one Gaussian per pixel
+                       (scenes.view_filling(seed=12, P=50_000, cover=True), 5.0, 12.0),            # 50k covering 1200x680
+                       (scenes.view_filling(seed=15, P=300_000, cam=scenes.TUM_FR1, anisotropic=True), 1.5, 4.0)]:
+        o = sc.oracle()
+        geo = o.geometry()
+        assert int((geo["radii"] > 0).sum()) == sc.P, sc.name
+        assert lo <= o.R / sc.P <= hi, (sc.name, o.R / sc.P)
+    room = scenes.room(P=50_000)
+    assert (room.oracle().geometry()["radii"] > 0).mean() < 0.1
