@@ -147,8 +147,9 @@ SB_API int sb_forward(const sb_settings* s, int P, const float* means3D, const f
 
 /* ---- sync-free forward (CUDA-graph capturable) -------------------------------------------------------------
  * Same work as sb_forward but num_rendered never leaves the device: the caller fixes a CAPACITY (tile
- * instances) for the binning workspace (sb_binning_workspace_bytes_ex(capacity, ...)); unused slots are padded
- * with a sentinel tile id and sorted to the end.  No memcpy to the host, no synchronisation, no allocation:
+ * instances) for the binning workspace (sb_binning_workspace_bytes_ex(capacity, ...)); the instance count is read
+ * on the device by the sort and the record gather, so only the live instances are processed.  No memcpy to the
+ * host, no synchronisation, no allocation:
  * the call (and sb_backward_ex with num_rendered := capacity) can be captured into a CUDA graph.
  * If the scene needs more than `capacity` instances the overflow flag (geometry workspace, int32 word 2) is set and
  * the images are written as NaN, so a truncated render cannot pass for a valid one;
